@@ -1,0 +1,147 @@
+/*
+ * jfem_b200.h -- C ABI of libjfem_b200.so: the B200 (sm_100a) implementation of JuliaFEM's
+ * 3D-elasticity hot path (element integration -> global scatter -> matrix-free / assembled
+ * K.u -> CG / Newton-Krylov).  This is the drop-in boundary: a Julia `ccall` shim
+ * (juliafem.jl_b200/julia/JuliaFEMB200.jl), the Python ctypes host (juliafem.jl_b200/_lib.py) and
+ * any other FFI bind exactly these symbols.  Plain pointers and sizes only; no torch types.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to JuliaFEM.jl):
+ *   ext = ext/JuliaFEMCUDAExt.jl,  cpu = src/backend/cpu.jl,  eas = src/element_assembly_structures.jl,
+ *   pe  = src/problems_elasticity.jl, sp = src/sparse/sparse.jl.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a JFEM_E* code otherwise; jfem_last_error() gives the
+ *     message (the reference throws Julia exceptions; the shim turns non-zero into error(msg)).
+ *     CG / Newton non-convergence is NOT an error (ext:630-631 only warns): status 0, iters = max.
+ *   - ids are the reference's: nodes 1..n_nodes, dof = 3*(node-1)+c, c=1..3 (src/assembly/problems.jl:476).
+ *     `index_base` (0 or 1) says what the caller's arrays use; Julia passes 1.
+ *   - all floating point is IEEE double.  Vectors are n_dofs = 3*n_nodes long, reference dof order.
+ *   - `on_device` != 0: vector pointers are CUDA device pointers on the handle's device, the call is
+ *     asynchronous on the handle's stream; == 0: host pointers, the call copies in/out and synchronises.
+ *   - host arrays stay owned by the caller; the library copies what it keeps.
+ *   - a handle is not thread-safe; different handles are independent (no global mutable state).
+ *   - there is no CPU fallback: without a usable CUDA device jfem_create fails with JFEM_ENODEV.
+ */
+#ifndef JFEM_B200_H
+#define JFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JFEM_ABI_VERSION 1
+
+/* status codes */
+#define JFEM_OK 0
+#define JFEM_EINVAL 1   /* bad argument (unsupported element type, id out of range, ...) */
+#define JFEM_ENODEV 2   /* no CUDA device / device not sm_100 capable */
+#define JFEM_ECUDA 3    /* CUDA runtime error */
+#define JFEM_ESTATE 4   /* call out of order (e.g. matvec before material is set) */
+#define JFEM_EDOMAIN 5  /* invalid deformation, J <= 0 (DomainError, src/materials/neo_hookean.jl:137) */
+#define JFEM_ENCCL 6    /* NCCL error */
+
+/* element types = nodes per element (Tet4, Hex8, Tet10; src/topology/tetrahedra.jl:73-105, hexahedra.jl:14-18) */
+#define JFEM_TET4 4
+#define JFEM_HEX8 8
+#define JFEM_TET10 10
+
+/* material kinds (src/materials/linear_elastic.jl, neo_hookean.jl, perfect_plasticity.jl) */
+#define JFEM_MAT_LINEAR_ELASTIC 0 /* params: E, nu */
+#define JFEM_MAT_NEO_HOOKEAN 1    /* params: E, nu  (mu, lambda derived as neo_hookean.jl:87-100); implies finite strain */
+#define JFEM_MAT_PERFECT_PLASTICITY 2 /* params: E, nu, sigma_y, H ; 13 state doubles per Gauss point */
+
+/* jfem_matvec / jfem_cg flags */
+#define JFEM_PROJECT 1      /* zero Dirichlet rows of the result (apply_dirichlet_kernel!, ext:423-435) */
+#define JFEM_TANGENT 2      /* operator = tangent K(u_lin) incl. geometric stiffness, not the linear-elastic K */
+#define JFEM_USE_CSR 4      /* CG / matvec through the assembled CSR matrix (cpu:221-254) instead of matrix-free */
+#define JFEM_JACOBI 8       /* opt-in 3x3 block-Jacobi preconditioner (not in the reference) */
+
+typedef struct jfem_handle jfem_handle;
+
+typedef struct jfem_info {
+    int32_t abi_version, device, elem_type, n_ranks;
+    int64_t n_nodes, n_elems, n_dofs, n_fixed;
+    int64_t n_patches, n_interface_nodes, n_affine_elems;
+    int64_t patch_elems, patch_max_nodes;
+    int64_t device_bytes;        /* device memory held by the handle */
+    int64_t matvec_launches;     /* kernel launches issued by the last jfem_matvec */
+    int64_t total_launches;      /* kernel launches issued since creation */
+    double setup_seconds;        /* host time spent building patches */
+} jfem_info;
+
+/* --- library ------------------------------------------------------------------------------ */
+int jfem_abi_version(void);
+const char *jfem_last_error(void);                 /* thread-local message of the last failing call */
+int jfem_device_count(int *count);
+
+/* --- problem setup: replaces initialize_gpu_data! (ext:86-217) ------------------------------ */
+/* coords: 3 x n_nodes column-major (x,y,z of node 1, then node 2, ...) as ext:114-123;
+ * conn: nnpe x n_elems column-major int32 (nodes of element 1, then element 2, ...) as ext:126-132. */
+int jfem_create(jfem_handle **out, int device, int elem_type, int64_t n_nodes, int64_t n_elems,
+                const double *coords, const int32_t *conn, int index_base);
+int jfem_destroy(jfem_handle *h);
+/* tuning knobs, before the first operator call: "patch_elems" (elements per thread-block patch),
+ * "deterministic" (1: ordered interface reduction [default], 0: fp64 atomics), "affine_fast_path" (1/0) */
+int jfem_set_option(jfem_handle *h, const char *key, double value);
+/* homogeneous material (per_element == 0: params has n_params entries) or per-element
+ * (per_element != 0: params is n_params x n_elems column-major), like E_vec/nu_vec of ext:135-141 */
+int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_params, int per_element);
+/* is_fixed / prescribed of ext:144-158.  dofs use index_base given at creation. */
+int jfem_set_dirichlet(jfem_handle *h, const int64_t *dofs, const double *values, int64_t n);
+int jfem_get_info(jfem_handle *h, jfem_info *info);
+/* run all later work of this handle on an existing CUDA stream (cudaStream_t passed as void*) */
+int jfem_set_stream(jfem_handle *h, void *cuda_stream);
+int jfem_synchronize(jfem_handle *h);
+
+/* --- matrix-free operator: replaces stiffness_operator_gpu / tangent_operator_gpu (ext:488-511),
+ *     matrix_vector_product (eas:307-309).  y = K x (pure K.v: fixes the f_ext defect at ext:468). */
+int jfem_matvec(jfem_handle *h, const double *x, double *y, int flags, int on_device);
+/* r = f_int(u) (compute_residual_gpu! ext:442-478 without the f_ext subtraction); for plasticity the
+ * trial state is kept aside until jfem_commit_state (src/materials/abstract_material.jl:203-207). */
+int jfem_internal_force(jfem_handle *h, const double *u, double *f_int, int flags, int on_device);
+int jfem_set_linearization(jfem_handle *h, const double *u, int on_device); /* u_current of ext:531-537 */
+int jfem_commit_state(jfem_handle *h);
+int jfem_get_state(jfem_handle *h, double *state /* 13 x ngp x n_elems */, int committed);
+int jfem_set_state(jfem_handle *h, const double *state);
+
+/* --- element matrices and assembled operator: replaces assemble_element! (pe:203-451),
+ *     add!(COO) + sparse() (sp:53-55,121-132) ------------------------------------------------- */
+/* Ke: ndof x ndof column-major per element, fe: ndof per element, elements [e0, e0+ne) in caller order (0-based e0) */
+int jfem_element_matrices(jfem_handle *h, const double *u /* may be NULL */, int64_t e0, int64_t ne, double *Ke, double *fe);
+int jfem_csr_size(jfem_handle *h, int64_t *n_rows, int64_t *nnz);
+/* rowptr (n_rows+1) and colind (nnz), index_base-based like the reference's colptr/rowval; host pointers */
+int jfem_csr_pattern(jfem_handle *h, int64_t *rowptr, int32_t *colind);
+/* assemble K(u) (+Kg for finite strain) into the handle's device CSR; vals/f_int (host or device, may be NULL) receive copies;
+ * symmetrise != 0 applies K <- (K+K')/2 (src/solvers.jl:289-292) */
+int jfem_assemble_csr(jfem_handle *h, const double *u, double *vals, double *f_int, int symmetrise, int on_device);
+int jfem_spmv(jfem_handle *h, const double *x, double *y, int flags, int on_device);
+
+/* --- solvers: replaces cg_solve_matfree_gpu! (ext:531-577) / cg_solve (cpu:221-254) and
+ *     solve_newton_krylov_gpu! (ext:685-854) --------------------------------------------------- */
+/* x: initial guess in, solution out.  Stop: sqrt(r.r) < tol (absolute, as the reference) or, if
+ * tol_is_relative, sqrt(r.r) <= tol*||b|| (projected b).  Fixed dofs of r and A.p are zeroed each iteration. */
+int jfem_cg(jfem_handle *h, const double *b, double *x, double tol, int tol_is_relative, int max_iter, int flags,
+            int *iters, double *resid, int on_device);
+/* history: 3 doubles per Newton step (cg_iters, ||R||, eta) like ElasticitySolution.history
+ * (src/backend/abstract.jl:138-145); eta = min(forcing_max, ||R||^forcing_power) (ext:819-820). */
+int jfem_newton_krylov(jfem_handle *h, const double *f_ext, double *u, double newton_tol, int max_newton,
+                       int max_cg_per_newton, double forcing_power, double forcing_max, int flags,
+                       int *newton_iters, int *cg_iters, double *resid, double *history, int history_cap, int on_device);
+
+/* --- multi-GPU (one process per GPU): replaces partition/halo of benchmarks/multigpu_mpi_benchmark.jl:120-360
+ *     and the MPI.Allreduce dots of demos/krylov_mpi_gpu_demo.jl:231-277 ------------------------- */
+int jfem_comm_unique_id(char *id128);  /* 128 bytes, to be broadcast by the host launcher */
+/* the handle was created on the LOCAL mesh (owned nodes first, then ghosts); n_owned nodes are owned. */
+int jfem_comm_init(jfem_handle *h, int n_ranks, int rank, const char *id128, int64_t n_owned_nodes);
+/* per neighbour: local node ids (index_base-based) to send / to receive into, both ascending global id */
+int jfem_comm_set_halo(jfem_handle *h, int n_neighbours, const int32_t *neighbour_rank,
+                       const int64_t *send_ptr, const int32_t *send_nodes,
+                       const int64_t *recv_ptr, const int32_t *recv_nodes);
+int jfem_comm_destroy(jfem_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JFEM_B200_H */

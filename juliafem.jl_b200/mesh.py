@@ -1,0 +1,250 @@
+"""Deterministic synthetic meshes, a minimal Abaqus reader and the node-range partitioner.
+
+Host-side helpers feeding the flat arrays the C ABI takes (include/jfem_b200.h).  All ids
+returned here are **1-based**, as at the reference's boundary (`Element.connectivity`,
+src/elements/elements.jl:72; dof = 3*(node-1)+c, src/assembly/problems.jl:476).
+
+Mesh definitions follow SURVEY.md §8(d):
+  * Hex8 lattice: node id (k-1)*nx*ny + (j-1)*nx + i, element (n1,n1+1,n1+1+nx,n1+nx,+nx*ny...)
+    exactly as benchmarks/multigpu_mpi_benchmark.jl:75-102 (`create_hex_mesh`, nx = #nodes in x).
+  * Tet10 lattice: P2 lattice of (2cx+1)(2cy+1)(2cz+1) nodes with the same x-fastest numbering,
+    every cell split into 6 Kuhn tets around the main diagonal, node order per
+    src/basis/lagrange_generated.jl:261-262 (5=(1-2) 6=(2-3) 7=(1-3) 8=(1-4) 9=(2-4) 10=(3-4)).
+  * partition: contiguous node ranges ceil(nn/P) + ghost elements, as
+    benchmarks/multigpu_mpi_benchmark.jl:120-229 (`partition_mesh_for_rank`).
+"""
+from __future__ import annotations
+
+import itertools
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+TET4, HEX8, TET10 = 4, 8, 10
+
+
+@dataclass
+class Mesh:
+    elem_type: int            # nodes per element: 4, 8, 10
+    coords: np.ndarray        # (n_nodes, 3) float64, row i = node id i+1
+    conn: np.ndarray          # (n_elems, nnpe) int32, 1-based node ids
+    node_sets: dict = field(default_factory=dict)
+    elem_sets: dict = field(default_factory=dict)
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.coords.shape[0])
+
+    @property
+    def n_elems(self) -> int:
+        return int(self.conn.shape[0])
+
+    @property
+    def n_dofs(self) -> int:
+        return 3 * self.n_nodes
+
+
+def hex8_lattice(nx: int, ny: int, nz: int, h: float = 1.0) -> Mesh:
+    """Structured Hex8 mesh on an nx*ny*nz NODE lattice (benchmarks/multigpu_mpi_benchmark.jl:75-102)."""
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    coords = np.stack([i.ravel() * h, j.ravel() * h, k.ravel() * h], axis=1).astype(np.float64)
+    ke, je, ie = np.meshgrid(np.arange(nz - 1), np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    n1 = (ke * nx * ny + je * nx + ie + 1).ravel().astype(np.int64)
+    n2 = n1 + 1
+    n3 = n2 + nx
+    n4 = n1 + nx
+    lay = nx * ny
+    conn = np.stack([n1, n2, n3, n4, n1 + lay, n2 + lay, n3 + lay, n4 + lay], axis=1).astype(np.int32)
+    return Mesh(HEX8, coords, conn)
+
+
+def _kuhn_tets():
+    """6 tets of the unit cell in doubled-integer corner coordinates, positively oriented."""
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        v = [np.zeros(3, dtype=np.int64)]
+        for ax in perm:
+            nxt = v[-1].copy()
+            nxt[ax] += 2
+            v.append(nxt)
+        v = np.array(v)
+        d = np.linalg.det((v[1:] - v[0]).astype(float))
+        if d < 0:
+            v[[2, 3]] = v[[3, 2]]
+        tets.append(v)
+    return np.array(tets)  # (6, 4, 3) in P2-lattice index units
+
+
+def tet10_kuhn(cx: int, cy: int, cz: int, lx: float = 1.0, ly: float | None = None, lz: float | None = None) -> Mesh:
+    """Tet10 mesh of a box with cx*cy*cz cells, 6 Kuhn tets per cell."""
+    ly = lx * cy / cx if ly is None else ly
+    lz = lx * cz / cx if lz is None else lz
+    px, py, pz = 2 * cx + 1, 2 * cy + 1, 2 * cz + 1
+    k, j, i = np.meshgrid(np.arange(pz), np.arange(py), np.arange(px), indexing="ij")
+    coords = np.stack([i.ravel() * (lx / (2 * cx)), j.ravel() * (ly / (2 * cy)), k.ravel() * (lz / (2 * cz))], axis=1)
+    tets = _kuhn_tets()                                  # (6,4,3)
+    edges = [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+    local = np.concatenate([tets, np.stack([(tets[:, a] + tets[:, b]) // 2 for a, b in edges], axis=1)], axis=1)  # (6,10,3)
+    ck, cj, ci = np.meshgrid(np.arange(cz), np.arange(cy), np.arange(cx), indexing="ij")
+    org = np.stack([2 * ci.ravel(), 2 * cj.ravel(), 2 * ck.ravel()], axis=1).astype(np.int64)  # (ncell,3)
+    idx = org[:, None, None, :] + local[None, :, :, :]   # (ncell,6,10,3)
+    ids = idx[..., 2] * (px * py) + idx[..., 1] * px + idx[..., 0] + 1
+    conn = ids.reshape(-1, 10).astype(np.int32)
+    return Mesh(TET10, coords.astype(np.float64), conn)
+
+
+def tet4_kuhn(cx: int, cy: int, cz: int, lx: float = 1.0) -> Mesh:
+    """Tet4 companion of tet10_kuhn (vertices only, compact numbering)."""
+    m = tet10_kuhn(cx, cy, cz, lx)
+    conn4 = m.conn[:, :4]
+    used = np.unique(conn4)
+    remap = np.zeros(m.n_nodes + 1, dtype=np.int32)
+    remap[used] = np.arange(1, used.size + 1, dtype=np.int32)
+    return Mesh(TET4, m.coords[used - 1], remap[conn4])
+
+
+_ABAQUS_TYPES = {"C3D4": TET4, "C3D10": TET10, "C3D8": HEX8}
+
+
+def read_abaqus_inp(path: str, elem_type: int | None = None) -> Mesh:
+    """Minimal Abaqus reader: *NODE, *ELEMENT (C3D4/C3D10/C3D8), *NSET/*ELSET (incl. GENERATE).
+
+    Mirrors what src/readers/parse_mesh.jl:8-60 / src/io/abaqus_reader.jl:13-67 extract for volume
+    elements.  Node ids are renumbered densely by sorted order, as the GPU extension does
+    (ext/JuliaFEMCUDAExt.jl:100-108)."""
+    nodes, elems, nsets, elsets = {}, {}, {}, {}
+    mode, et, cur, gen, pending = None, None, None, False, []
+    with open(path) as fh:
+        for raw in fh:
+            line = raw.strip()
+            if not line or line.startswith("**"):
+                continue
+            if line.startswith("*"):
+                pending = []
+                head = line.upper()
+                opts = dict(re.findall(r"(\w+)\s*=\s*([^,\s]+)", line, flags=re.I))
+                opts = {k.upper(): v for k, v in opts.items()}
+                if head.startswith("*NODE") and not head.startswith("*NODE "):
+                    mode = "node"
+                    cur = opts.get("NSET")
+                    if cur:
+                        nsets.setdefault(cur, [])
+                elif head.startswith("*ELEMENT"):
+                    t = opts.get("TYPE", "").upper()
+                    et = _ABAQUS_TYPES.get(t)
+                    mode = "elem" if et else None
+                    cur = opts.get("ELSET")
+                    if cur and et:
+                        elsets.setdefault(cur, [])
+                elif head.startswith("*NSET"):
+                    mode, cur, gen = "nset", opts.get("NSET"), "GENERATE" in head
+                    nsets.setdefault(cur, [])
+                elif head.startswith("*ELSET"):
+                    mode, cur, gen = "elset", opts.get("ELSET"), "GENERATE" in head
+                    elsets.setdefault(cur, [])
+                else:
+                    mode = None
+                continue
+            vals = [v for v in (s.strip() for s in line.split(",")) if v]
+            if mode == "node":
+                nid = int(vals[0])
+                nodes[nid] = [float(v) for v in vals[1:4]] + [0.0] * (4 - len(vals))
+                if cur:
+                    nsets[cur].append(nid)
+            elif mode == "elem":
+                pending += [int(v) for v in vals]
+                if len(pending) >= et + 1:
+                    elems[pending[0]] = (et, pending[1:et + 1])
+                    if cur:
+                        elsets[cur].append(pending[0])
+                    pending = []
+            elif mode in ("nset", "elset"):
+                tgt = nsets if mode == "nset" else elsets
+                if gen:
+                    a, b = int(vals[0]), int(vals[1])
+                    st = int(vals[2]) if len(vals) > 2 else 1
+                    tgt[cur] += list(range(a, b + 1, st))
+                else:
+                    tgt[cur] += [int(v) for v in vals if re.fullmatch(r"-?\d+", v)]
+    if elem_type is None:
+        kinds = {t for t, _ in elems.values()}
+        elem_type = max(kinds)
+    keep = sorted(eid for eid, (t, _) in elems.items() if t == elem_type)
+    used = sorted({n for eid in keep for n in elems[eid][1]})
+    remap = {n: i + 1 for i, n in enumerate(used)}
+    coords = np.array([nodes[n][:3] for n in used], dtype=np.float64)
+    conn = np.array([[remap[n] for n in elems[eid][1]] for eid in keep], dtype=np.int32)
+    eremap = {eid: i + 1 for i, eid in enumerate(keep)}
+    m = Mesh(elem_type, coords, conn)
+    m.node_sets = {k: np.array(sorted(remap[n] for n in v if n in remap), dtype=np.int64) for k, v in nsets.items()}
+    m.elem_sets = {k: np.array(sorted(eremap[e] for e in v if e in eremap), dtype=np.int64) for k, v in elsets.items()}
+    return m
+
+
+def clamp_dofs(mesh: Mesh, axis: int = 0, value: float = 0.0, tol: float = 1e-12) -> np.ndarray:
+    """1-based dof ids of all three components of nodes on the plane x_axis == value
+    (demos/cantilever_physics_gpu.jl:88-93 clamps x = 0)."""
+    nodes = np.nonzero(np.abs(mesh.coords[:, axis] - value) <= tol)[0].astype(np.int64)
+    return (3 * nodes[:, None] + np.arange(1, 4)[None, :]).ravel()
+
+
+def test_vector(n_dofs: int, fixed_dofs: np.ndarray | None = None, seed: int = 12345) -> np.ndarray:
+    """u = 1e-3*(2U-1), U ~ default_rng(12345).random(nDOF), fixed dofs zeroed."""
+    u = 1e-3 * (2.0 * np.random.default_rng(seed).random(n_dofs) - 1.0)
+    if fixed_dofs is not None and len(fixed_dofs):
+        u[np.asarray(fixed_dofs) - 1] = 0.0
+    return u
+
+
+@dataclass
+class Partition:
+    rank: int
+    n_ranks: int
+    owned_range: tuple          # (first, last) 1-based global node ids owned (inclusive)
+    local_nodes: np.ndarray     # global 1-based ids: owned (ascending) then ghosts (ascending)
+    n_owned: int
+    elems: np.ndarray           # global 0-based element indices computed on this rank
+    conn_local: np.ndarray      # (n_local_elems, nnpe) int32, 1-based LOCAL node ids
+    send: dict                  # neighbour rank -> local (1-based) owned node ids to send, ascending global id
+    recv: dict                  # neighbour rank -> local (1-based) ghost node ids to receive into, ascending global id
+
+
+def partition_mesh(mesh: Mesh, n_ranks: int, rank: int) -> Partition:
+    """Owner-computes partition with one layer of ghost elements
+    (benchmarks/multigpu_mpi_benchmark.jl:120-229): rank r owns the contiguous node-id range
+    [r*ceil(nn/P)+1, min((r+1)*ceil(nn/P), nn)]; local elements = those touching >= 1 owned node;
+    ghosts = their non-owned nodes, sorted ascending after the owned ones; rank r sends to s the
+    owned nodes that appear in s's ghost list (i.e. owned nodes of elements that also touch
+    s-owned nodes)."""
+    nn = mesh.n_nodes
+    per = -(-nn // n_ranks)
+    lo, hi = rank * per + 1, min((rank + 1) * per, nn)
+    owner = (mesh.conn.astype(np.int64) - 1) // per           # (ne, nnpe)
+    mine = (owner == rank).any(axis=1)
+    elems = np.nonzero(mine)[0]
+    c = mesh.conn[elems].astype(np.int64)
+    touched = np.unique(c)
+    ghosts = touched[(touched < lo) | (touched > hi)]
+    owned = np.arange(lo, hi + 1, dtype=np.int64)
+    local_nodes = np.concatenate([owned, ghosts])
+    g2l = np.zeros(nn + 1, dtype=np.int64)
+    g2l[local_nodes] = np.arange(1, local_nodes.size + 1)
+    conn_local = g2l[c].astype(np.int32)
+    recv, send = {}, {}
+    gown = (ghosts - 1) // per
+    for s in np.unique(gown):
+        recv[int(s)] = g2l[ghosts[gown == s]]
+    # what I must send to s: my owned nodes that are ghosts on s <=> owned nodes of elements touching s-owned nodes
+    oe = owner[elems]
+    for s in range(n_ranks):
+        if s == rank:
+            continue
+        has_s = (oe == s).any(axis=1)
+        if not has_s.any():
+            continue
+        cand = np.unique(c[has_s])
+        cand = cand[(cand >= lo) & (cand <= hi)]
+        if cand.size:
+            send[s] = g2l[cand]
+    return Partition(rank, n_ranks, (lo, hi), local_nodes, owned.size, elems, conn_local, send, recv)
