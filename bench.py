@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the hot path (BASELINE.json: Tet10 elasticity matvec GDOF/s).
+
+A "step" is ONE matrix-free K.u over the whole mesh (BASELINE.json configs[1]: T1, Tet10 cantilever 88x22x22 cells,
+1 075 275 DOF; for N GPUs the box grows to 88x22x(22N) cells and is slab-partitioned by contiguous node ranges, i.e.
+weak scaling).  Timed with CUDA events on the stream the kernels are launched on; L2 is flushed between timed steps
+(a 512 MiB buffer is overwritten), because the T1 working set (~40 MB) would otherwise sit in the 126 MB L2.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload T1|T10|H100|...]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = same metric through the C ABI with
+pinned HOST buffers (H2D + D2H inside the timed region), `roofline` = algorithmic bytes (35 B/DOF Tet10, 35.7 Hex8,
+SURVEY.md 8d) / measured step time vs the measured HBM peak, `cpu_baseline` = the CPU oracle timed on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {   # name: (elem_type, cells/nodes, box lengths)
+    "T1": (10, (88, 22, 22), (4.0, 1.0, 1.0)),        # 1 075 275 DOF  (configs[1])
+    "T10": (10, (192, 48, 48), (4.0, 1.0, 1.0)),      # 10 867 395 DOF
+    "TS": (10, (24, 6, 6), (4.0, 1.0, 1.0)),          # small smoke size
+    "H100": (8, (321, 321, 321), None),               # 99 228 483 DOF (configs[2]); nodes per direction
+    "H12": (8, (161, 161, 161), None),                # 12.5 M DOF
+}
+BYTES_PER_DOF = {10: 35.0, 8: 35.0 + 2.0 / 3.0, 4: 35.0}
+METRIC = "tet10_elasticity_matvec_gdofs"
+
+
+def build_mesh(name, n_gpus=1):
+    from juliafem.jl_b200 import mesh
+    et, dims, box = WORKLOADS[name]
+    if et == 10:
+        cx, cy, cz = dims
+        return mesh.tet10_kuhn(cx, cy, cz * n_gpus, box[0], box[1], box[2] * n_gpus)
+    nx, ny, nz = dims
+    return mesh.hex8_lattice(nx, ny, (nz - 1) * n_gpus + 1, 1.0 / (nx - 1))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(workload, seconds=12.0):
+    """The reference's CPU K.v is a sparse matrix-vector product on the assembled K
+    (src/element_assembly_structures.jl:307-309).  Timed with the oracle port on a bounded sample: a sub-box of the
+    workload (same element type, spacing, material) small enough that assembly + timing stay within ~10-30 s."""
+    from oracle import oracle as O
+    from juliafem.jl_b200 import mesh
+    et, dims, box = WORKLOADS[workload]
+    if et == 10:
+        m = mesh.tet10_kuhn(32, 12, 12, 4.0 * 32 / 88, 12 / 22, 12 / 22)
+        sample = "Tet10 32x12x12-cell sub-box of the workload (121 875 DOF): assembled CSR SpMV, OpenMP"
+    else:
+        m = mesh.hex8_lattice(49, 49, 49, 1.0 / 320)
+        sample = "Hex8 49^3-node sub-box (352 947 DOF): assembled CSR SpMV, OpenMP"
+    t0 = time.perf_counter()
+    rp, ci, vals, _ = O.assemble_csr(et, m.coords, m.conn, par=(210e9, 0.3))
+    t_asm = time.perf_counter() - t0
+    u = mesh.test_vector(m.n_dofs)
+    O.spmv(rp, ci, vals, u)
+    best, t_end, reps = 1e30, time.perf_counter() + min(seconds, 8.0), 0
+    while time.perf_counter() < t_end or reps < 3:
+        t0 = time.perf_counter()
+        O.spmv(rp, ci, vals, u)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    t0 = time.perf_counter()
+    O.matfree(et, m.coords, m.conn, u)
+    t_mf = time.perf_counter() - t0
+    return {"value": m.n_dofs / best / 1e9, "unit": "GDOF/s", "cores": O.num_threads(), "kind": "port",
+            "sample": sample + f"; best of {reps}; assembly of the sample took {t_asm:.2f} s ({m.n_elems / t_asm:.0f} elements/s); "
+                               f"matrix-free oracle K.u {m.n_dofs / t_mf / 1e9:.4f} GDOF/s"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia (not installed, and
+    the package does not load as shipped), so this arm times the oracle port of its CPU K.v with all host
+    threads, rank 0 only."""
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.workload, seconds=10.0)
+    steps_ms = 1e3 * 0.0
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload + " (bounded sample, see cpu_baseline.sample)"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="T1", choices=sorted(WORKLOADS))
+    ap.add_argument("--patch", type=int, default=0)
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from juliafem.jl_b200 import _lib, mesh
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = build_mesh(args.workload, world)
+    et = m.elem_type
+    fixed_g = mesh.clamp_dofs(m)
+    total_dofs = m.n_dofs
+    if world > 1:
+        part = mesh.partition_mesh(m, world, rank)
+        coords_l, conn_l = m.coords[part.local_nodes - 1], part.conn_local
+        h = _lib.Handle(et, coords_l, conn_l, device=local_rank)
+        g2l = np.zeros(m.n_nodes + 1, dtype=np.int64)
+        g2l[part.local_nodes] = np.arange(1, part.local_nodes.size + 1)
+        fn = (fixed_g - 1) // 3 + 1
+        keep = g2l[fn] > 0
+        fixed = 3 * (g2l[fn[keep]] - 1) + ((fixed_g[keep] - 1) % 3) + 1
+        n_local_dofs, n_own_dofs = 3 * part.local_nodes.size, 3 * part.n_owned
+    else:
+        h = _lib.Handle(et, m.coords, m.conn, device=local_rank)
+        fixed, n_local_dofs, n_own_dofs = fixed_g, m.n_dofs, m.n_dofs
+    if args.patch:
+        h.set_option("patch_elems", args.patch)
+    h.set_material(_lib.MAT_LINEAR_ELASTIC, (210e9, 0.3))
+    h.set_dirichlet(fixed)
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    if world > 1:
+        uid = [_lib.Handle.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=dev)
+        h.comm_init(world, rank, uid[0], part.n_owned)
+        h.comm_set_halo(part.send, part.recv)
+
+    u_full = mesh.test_vector(total_dofs, fixed_g)
+    u_host = u_full if world == 1 else u_full.reshape(-1, 3)[part.local_nodes - 1].ravel().copy()
+    x = torch.from_numpy(u_host).to(dev)
+    y = torch.empty_like(x)
+    flush = None if args.no_flush else torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        h.matvec(x, y, flags=_lib.PROJECT)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    info = h.info()
+    launches_per_step = int(info.matvec_launches) + (2 if world > 1 else 0)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(float(k))
+        if world > 1:
+            dist.barrier()
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    barrier()
+    times = np.array([a.elapsed_time(b) for a, b in ev])       # ms, device time of each step
+    ms = float(times.mean())
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the C ABI with pinned host buffers (H2D of x, D2H of y inside the timed region)
+    xh = torch.empty(n_local_dofs, dtype=torch.float64, pin_memory=True)
+    yh = torch.empty(n_local_dofs, dtype=torch.float64, pin_memory=True)
+    xh.copy_(torch.from_numpy(u_host))
+    xn, yn = xh.numpy(), yh.numpy()
+    n_e2e = max(3, min(args.steps, 20))
+    for _ in range(2):
+        h.matvec(xn, yn, flags=_lib.PROJECT)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        h.matvec(xn, yn, flags=_lib.PROJECT)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(np.abs(yn[:n_own_dofs]).sum())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        gdofs = total_dofs / (ms * 1e-3) / 1e9
+        ach = BYTES_PER_DOF[et] * total_dofs / world / (ms * 1e-3) / 1e9     # per GPU
+        out = {
+            "metric": METRIC, "value": gdofs, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {total_dofs} DOF, {m.n_elems} elements, "
+                                   f"linear elastic E=210e9 nu=0.3, clamp x=0, deterministic scatter",
+                       "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
+                       "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems),
+                       "partition": "z-slabs by contiguous node range, owner-computes + ghost elements" if world > 1 else "single GPU",
+                       "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds)},
+            "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
+                    "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_dof": BYTES_PER_DOF[et],
+                         "note": "achieved = algorithmic bytes of one K.u / CUDA-event time of the whole step (patch kernel + interface reduce)"},
+            "clocks": clocks,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                out["roofline"]["traffic"] = json.load(open(prof)).get(args.workload)
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(out), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

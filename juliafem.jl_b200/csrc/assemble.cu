@@ -1,0 +1,356 @@
+// assemble.cu -- element matrices, global CSR pattern + coloured scatter, SpMV.
+//
+// Replaces assemble_element! -> add!(SparseMatrixCOO) -> sparse() (src/problems_elasticity.jl:203-451,
+// src/sparse/sparse.jl:53-55,121-132).  The pattern is exactly the reference's: every (dof_i, dof_j) pair of every
+// element is stored, zeros included, rows = 3*(node-1)+c, column indices ascending.  Because the pattern is the
+// node-adjacency graph blown up by 3x3, it is built at node level on the host (sort + unique per node) and expanded
+// arithmetically:  rowptr[3n+c] = 9*adjptr[n] + 3*c*deg(n),  colind = 3*adj + d.
+// Values: one thread per (element, column j) applies the tangent functor of elem.cuh to the unit vector e_j, which
+// yields column j of Ke = Km(+Kg); elements are processed colour by colour (greedy colouring, the scheme of
+// src/preprocess.jl:331-398) so that the += into vals needs no atomics and the summation order is fixed.
+#include <algorithm>
+
+#include "elem.cuh"
+#include "handle.h"
+
+using namespace jf;
+
+// global-memory field accessor; base == nullptr means "unit vector e_(kj,cj)"
+struct AField {
+    const double *base;
+    const int *n;
+    int kj, cj;
+    __device__ __forceinline__ double operator()(int k, int c) const {
+        return base ? __ldg(base + 3 * (long long)n[k] + c) : ((k == kj && c == cj) ? 1.0 : 0.0);
+    }
+};
+
+template <int NNPE, class Pt, class OUT>
+__device__ __forceinline__ bool elem_dispatch(const Pt &pt, long long ei, const AField (&F)[Pt::NF], const AField &X, OUT &&out) {
+    if (NNPE == 10) return tet10_general(pt, ei, F, X, out);
+    if (NNPE == 8) return hex8_general(pt, ei, F, X, out);
+    return tet4_general(pt, ei, F, X, out);
+}
+
+struct AsmArgs {
+    const int32_t *conn;       // caller order, 0-based
+    const int32_t *elems;      // element list of this launch (nullptr: e0 + i)
+    long long e0, ne;
+    const double *coords, *u;
+    const long long *e2i;
+    const long long *adjptr;
+    const uint16_t *eblk;
+    double *vals;              // CSR values (scatter) ...
+    double *Ke;                // ... or dense per-element output (column-major), one of the two
+    int *fail;
+};
+
+template <int NNPE, class Pt>
+__global__ void __launch_bounds__(128) elem_columns_kernel(AsmArgs a, Pt pt) {
+    constexpr int ND = 3 * NNPE, NF = Pt::NF;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.ne * ND) return;
+    const long long i = idx / ND;
+    const int j = (int)(idx - i * ND), kj = j / 3, cj = j - 3 * kj;
+    const long long e = a.elems ? a.elems[a.e0 + i] : a.e0 + i;
+    int n[NNPE];
+    JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = a.conn[e * NNPE + k];
+    AField X{a.coords, n, 0, 0};
+    AField F[NF];
+    F[0] = AField{nullptr, n, kj, cj};
+    if (NF == 2) F[NF - 1] = AField{a.u, n, 0, 0};
+    bool ok;
+    if (a.vals) {
+        double *vals = a.vals;
+        const long long *adjptr = a.adjptr;
+        const uint16_t *blk = a.eblk + e * NNPE * NNPE;
+        auto out = [=](int k, int c, double v) {
+            const long long ap = adjptr[n[k]], deg = adjptr[n[k] + 1] - ap;
+            vals[9 * ap + 3 * c * deg + 3 * blk[k * NNPE + kj] + cj] += v;
+        };
+        ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
+    } else {
+        double *Ke = a.Ke + (i * ND + j) * ND;
+        auto out = [=](int k, int c, double v) { Ke[3 * k + c] = v; };
+        ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
+    }
+    if (!ok) atomicOr(a.fail, 1);
+}
+
+template <int NNPE, class Pt>
+__global__ void __launch_bounds__(128) elem_fint_kernel(AsmArgs a, Pt pt, double *fe) {
+    constexpr int ND = 3 * NNPE;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.ne) return;
+    const long long e = a.e0 + i;
+    int n[NNPE];
+    JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = a.conn[e * NNPE + k];
+    AField X{a.coords, n, 0, 0};
+    AField F[1] = {AField{a.u, n, 0, 0}};
+    double *o = fe + i * ND;
+    auto out = [=](int k, int c, double v) { o[3 * k + c] = v; };
+    bool ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
+    if (!ok) atomicOr(a.fail, 1);
+}
+
+__global__ void expand_pattern_kernel(long long n_nodes, const long long *__restrict__ adjptr, const int32_t *__restrict__ adj,
+                                      long long *__restrict__ rowptr, int32_t *__restrict__ colind) {
+    long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > n_nodes) return;
+    if (a == n_nodes) { rowptr[3 * n_nodes] = 9 * adjptr[n_nodes]; return; }
+    const long long ap = adjptr[a], deg = adjptr[a + 1] - ap;
+    for (int c = 0; c < 3; c++) {
+        const long long r0 = 9 * ap + 3 * c * deg;
+        rowptr[3 * a + c] = r0;
+        for (long long q = 0; q < deg; q++) {
+            const int32_t m = adj[ap + q];
+            colind[r0 + 3 * q] = 3 * m; colind[r0 + 3 * q + 1] = 3 * m + 1; colind[r0 + 3 * q + 2] = 3 * m + 2;
+        }
+    }
+}
+
+// K <- (K + K')/2  (src/solvers.jl:289-292); one thread per stored entry above the diagonal
+__global__ void symmetrise_kernel(long long n_rows, const long long *__restrict__ rowptr, const int32_t *__restrict__ colind, double *vals) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    for (long long p = rowptr[r]; p < rowptr[r + 1]; p++) {
+        const long long c = colind[p];
+        if (c <= r) continue;
+        long long lo = rowptr[c], hi = rowptr[c + 1];
+        while (lo < hi) { long long m = (lo + hi) >> 1; if (colind[m] < r) lo = m + 1; else hi = m; }
+        const double v = 0.5 * (vals[p] + vals[lo]);
+        vals[p] = v; vals[lo] = v;
+    }
+}
+
+// y = K x, one warp per row, fixed lane-strided order + shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) spmv_kernel(long long n_rows, const long long *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                                    const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y,
+                                                    const uint8_t *__restrict__ fixed, int project, const int *done) {
+    if (done && *done) return;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    double acc = 0;
+    for (long long p = rowptr[row] + lane; p < rowptr[row + 1]; p += 32) acc += vals[p] * __ldg(x + colind[p]);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = (project && fixed[row]) ? 0.0 : acc;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+int csr_build(jfem_handle *h) {
+    if (h->csr_built) return JFEM_OK;
+    JFEM_TRY(ensure_built(h));
+    const MeshHost &m = h->mesh;
+    const int nnpe = m.nnpe;
+    const int64_t nn = m.n_nodes, ne = m.n_elems;
+    // node -> elements
+    std::vector<int64_t> nptr(nn + 1, 0);
+    for (int64_t i = 0; i < ne * nnpe; i++) nptr[m.conn[i] + 1]++;
+    for (int64_t i = 0; i < nn; i++) nptr[i + 1] += nptr[i];
+    std::vector<int32_t> n2e(nptr[nn]);
+    {
+        std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
+        for (int64_t e = 0; e < ne; e++) for (int k = 0; k < nnpe; k++) n2e[fill[m.conn[e * nnpe + k]]++] = (int32_t)e;
+    }
+    // node adjacency
+    std::vector<int64_t> &ap = h->h_nadj_ptr;
+    ap.assign(nn + 1, 0);
+    std::vector<std::vector<int32_t>> tmp(nn);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t a = 0; a < nn; a++) {
+        std::vector<int32_t> &v = tmp[a];
+        v.reserve((nptr[a + 1] - nptr[a]) * nnpe);
+        for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) for (int k = 0; k < nnpe; k++) v.push_back(m.conn[(int64_t)n2e[q] * nnpe + k]);
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    for (int64_t a = 0; a < nn; a++) {
+        if (tmp[a].size() > 65535) { jfem_set_error("node %lld has more than 65535 neighbours", (long long)a); return JFEM_EINVAL; }
+        ap[a + 1] = ap[a] + (int64_t)tmp[a].size();
+    }
+    std::vector<int32_t> &adj = h->h_nadj;
+    adj.resize(ap[nn]);
+#pragma omp parallel for schedule(static)
+    for (int64_t a = 0; a < nn; a++) std::copy(tmp[a].begin(), tmp[a].end(), adj.begin() + ap[a]);
+    std::vector<std::vector<int32_t>>().swap(tmp);
+    // per element block positions
+    std::vector<uint16_t> eblk((size_t)ne * nnpe * nnpe);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; e++)
+        for (int k = 0; k < nnpe; k++) {
+            const int32_t a = m.conn[e * nnpe + k];
+            const int32_t *lo = &adj[ap[a]], *hi = &adj[ap[a + 1]];
+            for (int l = 0; l < nnpe; l++)
+                eblk[(e * nnpe + k) * nnpe + l] = (uint16_t)(std::lower_bound(lo, hi, m.conn[e * nnpe + l]) - lo);
+        }
+    // greedy colouring (src/preprocess.jl:331-398), elements visited in ascending id
+    std::vector<int32_t> colour(ne, -1);
+    int ncol = 0;
+    {
+        std::vector<uint8_t> used;
+        for (int64_t e = 0; e < ne; e++) {
+            used.assign(ncol + 1, 0);
+            for (int k = 0; k < nnpe; k++) {
+                const int32_t a = m.conn[e * nnpe + k];
+                for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) { int32_t c = colour[n2e[q]]; if (c >= 0) used[c] = 1; }
+            }
+            int c = 0;
+            while (used[c]) c++;
+            colour[e] = c;
+            if (c + 1 > ncol) ncol = c + 1;
+        }
+    }
+    h->colour_ptr.assign(ncol + 1, 0);
+    for (int64_t e = 0; e < ne; e++) h->colour_ptr[colour[e] + 1]++;
+    for (int c = 0; c < ncol; c++) h->colour_ptr[c + 1] += h->colour_ptr[c];
+    std::vector<int32_t> celems(ne);
+    {
+        std::vector<int64_t> fill(h->colour_ptr.begin(), h->colour_ptr.end() - 1);
+        for (int64_t e = 0; e < ne; e++) celems[fill[colour[e]]++] = (int32_t)e;
+    }
+    JFEM_TRY(h->nadj_ptr.upload(ap));
+    JFEM_TRY(h->nadj.upload(adj));
+    JFEM_TRY(h->eblk.upload(eblk));
+    JFEM_TRY(h->colour_elems.upload(celems));
+    JFEM_TRY(h->dconn.upload(m.conn));
+    const int64_t nnz = 9 * ap[nn];
+    JFEM_TRY(h->rowptr.alloc(3 * nn + 1));
+    JFEM_TRY(h->colind.alloc(nnz));
+    JFEM_TRY(h->vals.alloc(nnz));
+    expand_pattern_kernel<<<(unsigned)((nn + 1 + 127) / 128), 128, 0, h->stream>>>(nn, (const long long *)h->nadj_ptr.p, h->nadj.p, (long long *)h->rowptr.p, h->colind.p);
+    JFEM_CUDA(cudaGetLastError());
+    JFEM_CUDA(cudaStreamSynchronize(h->stream));
+    h->total_launches++;
+    h->csr_built = true;
+    return JFEM_OK;
+}
+
+static int ensure_dconn(jfem_handle *h) {
+    if (h->dconn.n == 0) JFEM_TRY(h->dconn.upload(h->mesh.conn));
+    return JFEM_OK;
+}
+
+template <int NNPE, class Pt>
+static int launch_columns(jfem_handle *h, AsmArgs a, const Pt &pt) {
+    const long long nthreads = a.ne * 3 * NNPE;
+    if (nthreads == 0) return JFEM_OK;
+    elem_columns_kernel<NNPE, Pt><<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(a, pt);
+    JFEM_CUDA(cudaGetLastError());
+    h->total_launches++;
+    return JFEM_OK;
+}
+
+template <int NNPE>
+static int columns_by_material(jfem_handle *h, AsmArgs a) {
+    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
+    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
+    const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; pt.la = la; pt.mu = mu; return launch_columns<NNPE>(h, a, pt); }
+    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; pt.la = la; pt.mu = mu; return launch_columns<NNPE>(h, a, pt); }
+    if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY) {
+        PtPPTangent pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.n_gp = n_gp;
+        return launch_columns<NNPE>(h, a, pt);
+    }
+    jfem_set_error("material not set");
+    return JFEM_ESTATE;
+}
+
+static int columns_dispatch(jfem_handle *h, AsmArgs a) {
+    switch (h->mesh.nnpe) {
+        case 10: return columns_by_material<10>(h, a);
+        case 8: return columns_by_material<8>(h, a);
+        default: return columns_by_material<4>(h, a);
+    }
+}
+
+static int check_fail(jfem_handle *h, const char *what) {
+    int fail = 0;
+    JFEM_CUDA(cudaMemcpyAsync(&fail, h->dflags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    JFEM_CUDA(cudaStreamSynchronize(h->stream));
+    if (fail) {
+        JFEM_CUDA(cudaMemset(h->dflags.p, 0, sizeof(int)));
+        jfem_set_error("Jacobian J = sqrt(det(C)) must be positive (invalid deformation in %s)", what);
+        return JFEM_EDOMAIN;
+    }
+    return JFEM_OK;
+}
+
+int csr_assemble(jfem_handle *h, const double *u, int symmetrise) {
+    JFEM_TRY(csr_build(h));
+    if (h->mat_kind != JFEM_MAT_LINEAR_ELASTIC && !u) { jfem_set_error("nonlinear material needs a displacement vector"); return JFEM_EINVAL; }
+    JFEM_CUDA(cudaMemsetAsync(h->vals.p, 0, h->vals.bytes(), h->stream));
+    AsmArgs a;
+    a.conn = h->dconn.p; a.elems = h->colour_elems.p; a.coords = h->coords.p; a.u = u; a.e2i = (const long long *)h->e2i.p;
+    a.adjptr = (const long long *)h->nadj_ptr.p; a.eblk = h->eblk.p; a.vals = h->vals.p; a.Ke = nullptr; a.fail = h->dflags.p;
+    for (size_t c = 0; c + 1 < h->colour_ptr.size(); c++) {
+        a.e0 = h->colour_ptr[c]; a.ne = h->colour_ptr[c + 1] - h->colour_ptr[c];
+        JFEM_TRY(columns_dispatch(h, a));
+    }
+    if (symmetrise) {
+        const long long nr = h->n_dofs();
+        symmetrise_kernel<<<(unsigned)((nr + 127) / 128), 128, 0, h->stream>>>(nr, (const long long *)h->rowptr.p, h->colind.p, h->vals.p);
+        JFEM_CUDA(cudaGetLastError());
+        h->total_launches++;
+    }
+    JFEM_TRY(check_fail(h, "assembly"));
+    h->vals_valid = true;
+    return JFEM_OK;
+}
+
+int csr_spmv(jfem_handle *h, const double *x, double *y, int flags, const int *done) {
+    if (!h->vals_valid) { jfem_set_error("jfem_assemble_csr has not been called"); return JFEM_ESTATE; }
+    const long long nr = h->n_dofs();
+    spmv_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, h->stream>>>(nr, (const long long *)h->rowptr.p, h->colind.p, h->vals.p, x, y, h->fixed.p,
+                                                                           (flags & JFEM_PROJECT) ? 1 : 0, done);
+    JFEM_CUDA(cudaGetLastError());
+    h->total_launches++;
+    h->matvec_launches = 1;
+    return JFEM_OK;
+}
+
+template <int NNPE>
+static int fint_by_material(jfem_handle *h, AsmArgs a, double *fe) {
+    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
+    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
+    const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
+    const unsigned blocks = (unsigned)((a.ne + 127) / 128);
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; pt.la = la; pt.mu = mu; elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
+    else if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHResidual pt; pt.la = la; pt.mu = mu; elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
+    else {
+        PtPPResidual pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.st_new = nullptr; pt.n_gp = n_gp;
+        elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe);
+    }
+    JFEM_CUDA(cudaGetLastError());
+    h->total_launches++;
+    return JFEM_OK;
+}
+
+// dense element matrices of elements [e0, e0+ne) in caller order (parity checks of Ke entries)
+int element_matrices(jfem_handle *h, const double *u, int64_t e0, int64_t ne, double *Ke, double *fe) {
+    JFEM_TRY(ensure_built(h));
+    JFEM_TRY(ensure_dconn(h));
+    if (h->mat_kind < 0) { jfem_set_error("jfem_set_material has not been called"); return JFEM_ESTATE; }
+    if (h->mat_kind != JFEM_MAT_LINEAR_ELASTIC && !u) { jfem_set_error("nonlinear material needs a displacement vector"); return JFEM_EINVAL; }
+    AsmArgs a;
+    a.conn = h->dconn.p; a.elems = nullptr; a.e0 = e0; a.ne = ne; a.coords = h->coords.p; a.u = u; a.e2i = (const long long *)h->e2i.p;
+    a.adjptr = nullptr; a.eblk = nullptr; a.vals = nullptr; a.Ke = Ke; a.fail = h->dflags.p;
+    if (Ke) JFEM_TRY(columns_dispatch(h, a));
+    if (fe) {
+        if (!u) { JFEM_CUDA(cudaMemsetAsync(fe, 0, sizeof(double) * ne * 3 * h->mesh.nnpe, h->stream)); }
+        else switch (h->mesh.nnpe) {
+            case 10: JFEM_TRY(fint_by_material<10>(h, a, fe)); break;
+            case 8: JFEM_TRY(fint_by_material<8>(h, a, fe)); break;
+            default: JFEM_TRY(fint_by_material<4>(h, a, fe)); break;
+        }
+    }
+    return check_fail(h, "element integration");
+}
+
+int jacobi_build(jfem_handle *h, int flags) {
+    (void)flags;
+    jfem_set_error("JFEM_JACOBI preconditioner is not implemented in this build");
+    (void)h;
+    return JFEM_EINVAL;
+}

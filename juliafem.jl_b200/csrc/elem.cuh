@@ -1,0 +1,431 @@
+// elem.cuh -- per-element device arithmetic (one thread = one element), fp64, registers only.
+//
+// What is computed is the reference's element integration (src/problems_elasticity.jl:245-409):
+//   J = sum_i dN_i (x) X_i, grad_i = inv(J).dN_i, grad(u) = sum_k u_k (x) grad_k   (src/basis/math.jl:47-54,198-201,249-255)
+//   f_k += w * P . grad_k  with w = weight*det(J)                                   (problems_elasticity.jl:248,407-409)
+// but never through the 6 x ndof BL matrix: gradients are taken in reference space and pushed through
+// inv(J) (3x3), and the Tet10 shape-function derivatives are used in barycentric form
+//   dN_a/dL_b = delta_ab (4 L_a - 1),  dN_ab/dL_a = 4 L_b      (same polynomials as lagrange_generated.jl:275-282)
+// which turns the 10x3 derivative table at the four GLTET4 points (src/quadrature/gltet.jl:18-25) into
+// "base + one extra term" updates.  Point functors (`Pt`) supply the constitutive map grad(u) -> P.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace jf {
+
+#define JF_UNROLL _Pragma("unroll")
+
+// GLTET4 abscissae (5+3*sqrt(5))/20 and (5-sqrt(5))/20
+#define T10_A 0.58541019662496845
+#define T10_B 0.13819660112501052
+
+__host__ __device__ constexpr int t10_edge(int a, int b) {
+    // mid-edge node of vertices a != b; order 4=(0-1) 5=(1-2) 6=(0-2) 7=(0-3) 8=(1-3) 9=(2-3)  (lagrange_generated.jl:261-262)
+    return (a < b ? a : b) == 0 ? ((a < b ? b : a) == 1 ? 4 : ((a < b ? b : a) == 2 ? 6 : 7))
+         : (a < b ? a : b) == 1 ? ((a < b ? b : a) == 2 ? 5 : 8)
+                                : 9;
+}
+
+__device__ __forceinline__ double inv3x3(const double (&J)[3][3], double (&iJ)[3][3]) {
+    double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    double r = 1.0 / det;
+    iJ[0][0] = c00 * r; iJ[1][0] = c01 * r; iJ[2][0] = c02 * r;
+    iJ[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+    iJ[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+    iJ[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+    iJ[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+    iJ[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+    iJ[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+    return det;
+}
+
+// field accessor over shared memory: value of component c at local element node k
+struct SField {
+    const double *base;   // 3 doubles per patch node
+    const int *n;         // local node index of the element's nodes
+    __device__ __forceinline__ double operator()(int k, int c) const { return base[3 * n[k] + c]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Point functors: P[i][j] from displacement gradients.  G[f][i][j] = d(field f)_i / dx_j.
+// ------------------------------------------------------------------------------------------------
+
+// sigma = la tr(eps) I + 2 mu eps  (src/materials/linear_elastic.jl:136-158; problems_elasticity.jl:313-332)
+struct PtLinear {
+    static constexpr int NF = 1;
+    double la, mu;
+    __device__ __forceinline__ bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
+        double tr = la * (G[0][0][0] + G[0][1][1] + G[0][2][2]);
+        double s01 = mu * (G[0][0][1] + G[0][1][0]), s12 = mu * (G[0][1][2] + G[0][2][1]), s02 = mu * (G[0][0][2] + G[0][2][0]);
+        P[0][0] = tr + 2 * mu * G[0][0][0]; P[1][1] = tr + 2 * mu * G[0][1][1]; P[2][2] = tr + 2 * mu * G[0][2][2];
+        P[0][1] = P[1][0] = s01; P[1][2] = P[2][1] = s12; P[0][2] = P[2][0] = s02;
+        return true;
+    }
+};
+
+__device__ __forceinline__ void sym6_to_33(const double (&s)[6], double (&S)[3][3]) {
+    S[0][0] = s[0]; S[1][1] = s[1]; S[2][2] = s[2];
+    S[0][1] = S[1][0] = s[3]; S[1][2] = S[2][1] = s[4]; S[0][2] = S[2][0] = s[5];
+}
+
+// Compressible Neo-Hookean, psi = mu/2 (I1-3) - mu ln J + la/2 ln^2 J  (src/materials/neo_hookean.jl:129-143).
+// S = 2 dpsi/dC = mu (I - C^-1) + la lnJ C^-1 ;  DD = 4 d2psi/dC2 = la Ci(x)Ci + 2(mu - la lnJ) I_{Ci}
+// (closed form of the Tensors.hessian call at neo_hookean.jl:222).  Total Lagrangian: P = F S,
+// dP = dF S + F (DD : sym(F' dF))  -- material + geometric stiffness (problems_elasticity.jl:270-289,378-404).
+struct NHCommon {
+    double la, mu;
+    __device__ __forceinline__ bool kin(const double (&Gu)[3][3], double (&F)[3][3], double (&Ci)[3][3], double &lnJ) const {
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) F[i][j] = Gu[i][j] + (i == j ? 1.0 : 0.0);
+        double C[3][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) C[i][j] = F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j];
+        double d = inv3x3(C, Ci);
+        lnJ = 0.5 * log(d);
+        return d > 0.0;
+    }
+};
+
+struct PtNHResidual : NHCommon {
+    static constexpr int NF = 1;
+    __device__ __forceinline__ bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
+        double F[3][3], Ci[3][3], lnJ;
+        bool ok = kin(G[0], F, Ci, lnJ);
+        double S[3][3];
+        double c = la * lnJ - mu;
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) S[i][j] = (i == j ? mu : 0.0) + c * Ci[i][j];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) P[i][j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
+        return ok;
+    }
+};
+
+struct PtNHTangent : NHCommon {   // field 0 = v (direction), field 1 = u (linearisation point)
+    static constexpr int NF = 2;
+    __device__ __forceinline__ bool eval(long long, const double (&G)[2][3][3], double (&P)[3][3]) const {
+        double F[3][3], Ci[3][3], lnJ;
+        bool ok = kin(G[1], F, Ci, lnJ);
+        double c = la * lnJ - mu;
+        double S[3][3], dE[3][3], A[3][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) S[i][j] = (i == j ? mu : 0.0) + c * Ci[i][j];
+        // A = F' dF ; dE = sym(A)
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) A[i][j] = F[0][i] * G[0][0][j] + F[1][i] * G[0][1][j] + F[2][i] * G[0][2][j];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) dE[i][j] = 0.5 * (A[i][j] + A[j][i]);
+        // dS = la (Ci:dE) Ci + 2 (mu - la lnJ) Ci dE Ci
+        double tr = 0;
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) tr += Ci[i][j] * dE[i][j];
+        double B[3][3], dS[3][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) B[i][j] = Ci[i][0] * dE[0][j] + Ci[i][1] * dE[1][j] + Ci[i][2] * dE[2][j];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+            dS[i][j] = la * tr * Ci[i][j] - 2.0 * c * (B[i][0] * Ci[0][j] + B[i][1] * Ci[1][j] + B[i][2] * Ci[2][j]);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+            P[i][j] = G[0][i][0] * S[0][j] + G[0][i][1] * S[1][j] + G[0][i][2] * S[2][j] + F[i][0] * dS[0][j] + F[i][1] * dS[1][j] + F[i][2] * dS[2][j];
+        return ok;
+    }
+};
+
+// J2 plasticity with linear kinematic hardening, radial return (src/materials/perfect_plasticity.jl:247-341).
+// State per Gauss point, SoA: st[s * n_gp + gp], s = 0..12 (eps_p 11,22,33,12,23,13 ; alpha ; kappa).
+struct PPCommon {
+    double la, mu, sy, H;
+    const double *st_old;
+    long long n_gp;
+    // returns true if plastic; s = stress (tensor comps), n = flow direction s_trial/q, dl = plastic multiplier
+    __device__ __forceinline__ bool ret_map(long long gp, const double (&e)[6], double (&s)[6], double (&n)[6], double &dl) const {
+        double ee[6], al[6];
+        JF_UNROLL for (int i = 0; i < 6; i++) { ee[i] = e[i] - st_old[i * n_gp + gp]; al[i] = st_old[(6 + i) * n_gp + gp]; }
+        double tr = la * (ee[0] + ee[1] + ee[2]);
+        JF_UNROLL for (int i = 0; i < 3; i++) s[i] = tr + 2 * mu * ee[i];
+        JF_UNROLL for (int i = 3; i < 6; i++) s[i] = 2 * mu * ee[i];
+        double sd[6];
+        JF_UNROLL for (int i = 0; i < 6; i++) sd[i] = s[i] - al[i];
+        double m = (sd[0] + sd[1] + sd[2]) / 3.0;
+        sd[0] -= m; sd[1] -= m; sd[2] -= m;
+        double nn = sd[0] * sd[0] + sd[1] * sd[1] + sd[2] * sd[2] + 2 * (sd[3] * sd[3] + sd[4] * sd[4] + sd[5] * sd[5]);
+        double q = sqrt(3.0 / 2.0) * sqrt(nn);
+        double f = q - sy;
+        if (f <= 0.0) { dl = 0.0; JF_UNROLL for (int i = 0; i < 6; i++) n[i] = 0.0; return false; }
+        JF_UNROLL for (int i = 0; i < 6; i++) n[i] = sd[i] / q;
+        dl = f / (2 * mu + (2.0 / 3.0) * H);
+        JF_UNROLL for (int i = 0; i < 6; i++) s[i] -= 2 * mu * dl * n[i];
+        return true;
+    }
+};
+
+__device__ __forceinline__ void strain6(const double (&G)[3][3], double (&e)[6]) {
+    e[0] = G[0][0]; e[1] = G[1][1]; e[2] = G[2][2];
+    e[3] = 0.5 * (G[0][1] + G[1][0]); e[4] = 0.5 * (G[1][2] + G[2][1]); e[5] = 0.5 * (G[0][2] + G[2][0]);
+}
+
+struct PtPPResidual : PPCommon {   // also writes the trial state (commit-on-convergence, abstract_material.jl:203-207)
+    static constexpr int NF = 1;
+    double *st_new;
+    __device__ __forceinline__ bool eval(long long gp, const double (&G)[1][3][3], double (&P)[3][3]) const {
+        double e[6], s[6], n[6], dl;
+        strain6(G[0], e);
+        bool pl = ret_map(gp, e, s, n, dl);
+        if (st_new) {
+            JF_UNROLL for (int i = 0; i < 6; i++) {
+                st_new[i * n_gp + gp] = st_old[i * n_gp + gp] + dl * n[i];
+                st_new[(6 + i) * n_gp + gp] = st_old[(6 + i) * n_gp + gp] + (2.0 / 3.0) * H * dl * n[i];
+            }
+            st_new[12 * n_gp + gp] = st_old[12 * n_gp + gp] + dl;
+        }
+        (void)pl;
+        sym6_to_33(s, P);
+        return true;
+    }
+};
+
+struct PtPPTangent : PPCommon {   // field 0 = v, field 1 = u;  dP = DD_ep : sym(grad v)
+    static constexpr int NF = 2;
+    __device__ __forceinline__ bool eval(long long gp, const double (&G)[2][3][3], double (&P)[3][3]) const {
+        double e[6], s[6], n[6], dl, de[6], ds[6];
+        strain6(G[1], e);
+        bool pl = ret_map(gp, e, s, n, dl);
+        strain6(G[0], de);
+        double tr = la * (de[0] + de[1] + de[2]);
+        JF_UNROLL for (int i = 0; i < 3; i++) ds[i] = tr + 2 * mu * de[i];
+        JF_UNROLL for (int i = 3; i < 6; i++) ds[i] = 2 * mu * de[i];
+        if (pl) {   // DD = DD_e - 4 mu^2/(2 mu + 2H/3) n (x) n   (perfect_plasticity.jl:337)
+            double nd = n[0] * de[0] + n[1] * de[1] + n[2] * de[2] + 2 * (n[3] * de[3] + n[4] * de[4] + n[5] * de[5]);
+            double c = 4 * mu * mu / (2 * mu + (2.0 / 3.0) * H) * nd;
+            JF_UNROLL for (int i = 0; i < 6; i++) ds[i] -= c * n[i];
+        }
+        sym6_to_33(ds, P);
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Tet10, isoparametric (valid for curved elements), GLTET4.  F[f] are the NF fields to differentiate,
+// X the coordinates; out(k, c, value) receives the element vector.  Returns false on invalid deformation.
+// ------------------------------------------------------------------------------------------------
+template <class Pt, class FLD, class OUT>
+__device__ __forceinline__ bool tet10_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+    constexpr int NF = Pt::NF;
+    const double c1 = 4.0 * T10_B - 1.0, c4b = 4.0 * T10_B, k4 = 4.0 * (T10_A - T10_B);
+    double bx[4][3], bu[NF][4][3];
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int c = 0; c < 3; c++) {
+        double sx = 0;
+        JF_UNROLL for (int b = 0; b < 4; b++) if (b != a) sx += X(t10_edge(a, b), c);
+        bx[a][c] = c1 * X(a, c) + c4b * sx;
+        JF_UNROLL for (int f = 0; f < NF; f++) {
+            double su = 0;
+            JF_UNROLL for (int b = 0; b < 4; b++) if (b != a) su += F[f](t10_edge(a, b), c);
+            bu[f][a][c] = c1 * F[f](a, c) + c4b * su;
+        }
+    }
+    double ST[4][3], fo[10][3];
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int c = 0; c < 3; c++) ST[a][c] = 0.0;
+    bool ok = true;
+    JF_UNROLL for (int g = 0; g < 4; g++) {
+        const int s = (g + 1) & 3;   // GLTET4 point g has L_s = A, the other three = B
+        double q0[3], J[3][3], iJ[3][3];
+        JF_UNROLL for (int c = 0; c < 3; c++) q0[c] = bx[0][c] + k4 * X(s == 0 ? 0 : t10_edge(0, s), c);
+        JF_UNROLL for (int a = 1; a < 4; a++) JF_UNROLL for (int c = 0; c < 3; c++)
+            J[a - 1][c] = bx[a][c] + k4 * X(a == s ? a : t10_edge(a, s), c) - q0[c];     // J[a][b] = dx_b/dxi_a
+        double det = inv3x3(J, iJ);
+        double w = det * (1.0 / 24.0);
+        double G[NF][3][3];
+        JF_UNROLL for (int f = 0; f < NF; f++) {
+            double h0[3], Hh[3][3];
+            JF_UNROLL for (int c = 0; c < 3; c++) h0[c] = bu[f][0][c] + k4 * F[f](s == 0 ? 0 : t10_edge(0, s), c);
+            JF_UNROLL for (int a = 1; a < 4; a++) JF_UNROLL for (int c = 0; c < 3; c++)
+                Hh[a - 1][c] = bu[f][a][c] + k4 * F[f](a == s ? a : t10_edge(a, s), c) - h0[c];  // H[a][i] = du_i/dxi_a
+            JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+                G[f][i][j] = iJ[j][0] * Hh[0][i] + iJ[j][1] * Hh[1][i] + iJ[j][2] * Hh[2][i];
+        }
+        double P[3][3];
+        ok &= pt.eval(elem * 4 + g, G, P);
+        // T_b[i] = w * sum_j P_ij gradL_b[j];  gradL_{c+1}[j] = iJ[j][c], gradL_0 = -sum
+        double T[4][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) {
+            JF_UNROLL for (int c = 0; c < 3; c++) T[c + 1][i] = w * (P[i][0] * iJ[0][c] + P[i][1] * iJ[1][c] + P[i][2] * iJ[2][c]);
+            T[0][i] = -(T[1][i] + T[2][i] + T[3][i]);
+        }
+        JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int i = 0; i < 3; i++) ST[a][i] += T[a][i];
+        JF_UNROLL for (int i = 0; i < 3; i++) fo[s][i] = k4 * T[s][i];
+        JF_UNROLL for (int a = 0; a < 4; a++) if (a != s) {
+            const int e = t10_edge(a, s);
+            const bool first = ((s + 3) & 3) < ((a + 3) & 3);   // GP order visits s = 1,2,3,0
+            JF_UNROLL for (int i = 0; i < 3; i++) fo[e][i] = first ? k4 * T[a][i] : fo[e][i] + k4 * T[a][i];
+        }
+    }
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int i = 0; i < 3; i++) out(a, i, fo[a][i] + c1 * ST[a][i]);
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int b = a + 1; b < 4; b++) JF_UNROLL for (int i = 0; i < 3; i++)
+        out(t10_edge(a, b), i, fo[t10_edge(a, b)][i] + c4b * (ST[a][i] + ST[b][i]));
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tet10 with affine geometry + linear elasticity: grad(u) is linear over the element, so the GLTET4 sum
+// (exact for the quadratic integrand) is replaced by its closed form on vertex values:
+//   G_c   = grad u at vertex c = 4 (u_c (x) g_c + sum_{a!=c} u_ac (x) g_a) - sum_a u_a (x) g_a ,  g_a = grad L_a
+//   f_a   = V/20 (4 sigma_a - S) g_a ,  f_ab = V/5 ((S + sigma_b) g_a + (S + sigma_a) g_b) ,  S = sum_c sigma_c
+// Only the 4 vertex coordinates are read.
+// ------------------------------------------------------------------------------------------------
+template <class FLD, class OUT>
+__device__ __forceinline__ void tet10_affine_linear(double la, double mu, const FLD &U, const FLD &X, OUT &&out) {
+    double J[3][3], iJ[3][3];
+    JF_UNROLL for (int a = 0; a < 3; a++) JF_UNROLL for (int c = 0; c < 3; c++) J[a][c] = X(a + 1, c) - X(0, c);
+    double det = inv3x3(J, iJ);
+    double g[4][3];
+    JF_UNROLL for (int j = 0; j < 3; j++) {
+        g[1][j] = iJ[j][0]; g[2][j] = iJ[j][1]; g[3][j] = iJ[j][2];
+        g[0][j] = -(iJ[j][0] + iJ[j][1] + iJ[j][2]);
+    }
+    double W[3][3];
+    JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+        W[i][j] = U(0, i) * g[0][j] + U(1, i) * g[1][j] + U(2, i) * g[2][j] + U(3, i) * g[3][j];
+    double sg[4][6];   // vertex stresses, 11 22 33 12 23 13
+    JF_UNROLL for (int c = 0; c < 4; c++) {
+        double G[3][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) {
+            double uc = 4.0 * U(c, i);
+            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] = uc * g[c][j] - W[i][j];
+        }
+        JF_UNROLL for (int a = 0; a < 4; a++) if (a != c) JF_UNROLL for (int i = 0; i < 3; i++) {
+            double ue = 4.0 * U(t10_edge(a, c), i);
+            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] += ue * g[a][j];
+        }
+        double tr = la * (G[0][0] + G[1][1] + G[2][2]);
+        sg[c][0] = tr + 2 * mu * G[0][0]; sg[c][1] = tr + 2 * mu * G[1][1]; sg[c][2] = tr + 2 * mu * G[2][2];
+        sg[c][3] = mu * (G[0][1] + G[1][0]); sg[c][4] = mu * (G[1][2] + G[2][1]); sg[c][5] = mu * (G[0][2] + G[2][0]);
+    }
+    const double V = det * (1.0 / 6.0), v20 = V * (1.0 / 20.0), v5 = V * (1.0 / 5.0);
+    double S[6];
+    JF_UNROLL for (int q = 0; q < 6; q++) S[q] = sg[0][q] + sg[1][q] + sg[2][q] + sg[3][q];
+    auto mulsym = [](const double (&s)[6], const double (&v)[3], double (&r)[3]) {
+        r[0] = s[0] * v[0] + s[3] * v[1] + s[5] * v[2];
+        r[1] = s[3] * v[0] + s[1] * v[1] + s[4] * v[2];
+        r[2] = s[5] * v[0] + s[4] * v[1] + s[2] * v[2];
+    };
+    JF_UNROLL for (int a = 0; a < 4; a++) {
+        double m[6], r[3];
+        JF_UNROLL for (int q = 0; q < 6; q++) m[q] = v20 * (4.0 * sg[a][q] - S[q]);
+        mulsym(m, g[a], r);
+        JF_UNROLL for (int i = 0; i < 3; i++) out(a, i, r[i]);
+    }
+    double Q[4][6];
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int q = 0; q < 6; q++) Q[a][q] = v5 * (S[q] + sg[a][q]);
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int b = a + 1; b < 4; b++) {
+        double r1[3], r2[3];
+        mulsym(Q[b], g[a], r1);
+        mulsym(Q[a], g[b], r2);
+        JF_UNROLL for (int i = 0; i < 3; i++) out(t10_edge(a, b), i, r1[i] + r2[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tet4, GLTET1 (src/quadrature/gltet.jl:7-11): constant gradient.
+// ------------------------------------------------------------------------------------------------
+template <class Pt, class FLD, class OUT>
+__device__ __forceinline__ bool tet4_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+    constexpr int NF = Pt::NF;
+    double J[3][3], iJ[3][3];
+    JF_UNROLL for (int a = 0; a < 3; a++) JF_UNROLL for (int c = 0; c < 3; c++) J[a][c] = X(a + 1, c) - X(0, c);
+    double det = inv3x3(J, iJ);
+    double G[NF][3][3];
+    JF_UNROLL for (int f = 0; f < NF; f++) {
+        double Hh[3][3];
+        JF_UNROLL for (int a = 0; a < 3; a++) JF_UNROLL for (int c = 0; c < 3; c++) Hh[a][c] = F[f](a + 1, c) - F[f](0, c);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+            G[f][i][j] = iJ[j][0] * Hh[0][i] + iJ[j][1] * Hh[1][i] + iJ[j][2] * Hh[2][i];
+    }
+    double P[3][3];
+    bool ok = pt.eval(elem, G, P);
+    double w = det * (1.0 / 6.0);
+    JF_UNROLL for (int i = 0; i < 3; i++) {
+        double t1 = w * (P[i][0] * iJ[0][0] + P[i][1] * iJ[1][0] + P[i][2] * iJ[2][0]);
+        double t2 = w * (P[i][0] * iJ[0][1] + P[i][1] * iJ[1][1] + P[i][2] * iJ[2][1]);
+        double t3 = w * (P[i][0] * iJ[0][2] + P[i][1] * iJ[1][2] + P[i][2] * iJ[2][2]);
+        out(0, i, -(t1 + t2 + t3)); out(1, i, t1); out(2, i, t2); out(3, i, t3);
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hex8, trilinear isoparametric, GLHEX8 (+-1/sqrt(3), weight 1; src/quadrature/quaddata.jl:4-5).
+// Reference-space derivatives through the modal (1,u,v,w,uv,uw,vw,uvw) coefficients of each field:
+// d/du at (.,v,w) = c1 + c4 v + c5 w + c7 v w, so the 8 Gauss-point gradients of a field cost ~60 flops
+// instead of 8 x 8 x 3.  Node order (-,-,-),(+,-,-),(+,+,-),(-,+,-),(-,-,+),... (lagrange_generated.jl:289-290).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hex8_modal(const double (&q)[8], double (&m)[8]) {
+    // m = 1/8 * sum_i sign_i * q_i for monomials 1,u,v,w,uv,uw,vw,uvw
+    double a0 = q[0] + q[1], a1 = q[1] - q[0], a2 = q[3] + q[2], a3 = q[2] - q[3];
+    double a4 = q[4] + q[5], a5 = q[5] - q[4], a6 = q[7] + q[6], a7 = q[6] - q[7];
+    // v-direction: (a0: v=-1 , a2: v=+1) etc.
+    double b0 = a0 + a2, b1 = a1 + a3, b2 = a2 - a0, b3 = a3 - a1;
+    double b4 = a4 + a6, b5 = a5 + a7, b6 = a6 - a4, b7 = a7 - a5;
+    m[0] = 0.125 * (b0 + b4); m[1] = 0.125 * (b1 + b5); m[2] = 0.125 * (b2 + b6); m[4] = 0.125 * (b3 + b7);
+    m[3] = 0.125 * (b4 - b0); m[5] = 0.125 * (b5 - b1); m[6] = 0.125 * (b6 - b2); m[7] = 0.125 * (b7 - b3);
+}
+
+#define HEX_GA 0.5773502691896258
+
+template <class Pt, class FLD, class OUT>
+__device__ __forceinline__ bool hex8_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+    constexpr int NF = Pt::NF;
+    double mx[3][8], mu_[NF][3][8];
+    JF_UNROLL for (int c = 0; c < 3; c++) {
+        double q[8];
+        JF_UNROLL for (int k = 0; k < 8; k++) q[k] = X(k, c);
+        hex8_modal(q, mx[c]);
+        JF_UNROLL for (int f = 0; f < NF; f++) {
+            JF_UNROLL for (int k = 0; k < 8; k++) q[k] = F[f](k, c);
+            hex8_modal(q, mu_[f][c]);
+        }
+    }
+    // modal accumulators of the transposed operation: R[i][a][m] collects sum_g P_g[i][a] * (dmonomial/dxi_a)(xi_g)
+    double Ru[3][4], Rv[3][4], Rw[3][4];   // for d/du: coefficients of (1, v, w, vw); d/dv: (1,u,w,uw); d/dw: (1,u,v,uv)
+    JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int m = 0; m < 4; m++) { Ru[i][m] = 0; Rv[i][m] = 0; Rw[i][m] = 0; }
+    bool ok = true;
+    JF_UNROLL for (int g = 0; g < 8; g++) {   // first index fastest (glquad.jl:12-15)
+        const double u = (g & 1) ? HEX_GA : -HEX_GA, v = (g & 2) ? HEX_GA : -HEX_GA, w = (g & 4) ? HEX_GA : -HEX_GA;
+        double J[3][3], iJ[3][3];
+        JF_UNROLL for (int c = 0; c < 3; c++) {
+            J[0][c] = mx[c][1] + mx[c][4] * v + mx[c][5] * w + mx[c][7] * (v * w);
+            J[1][c] = mx[c][2] + mx[c][4] * u + mx[c][6] * w + mx[c][7] * (u * w);
+            J[2][c] = mx[c][3] + mx[c][5] * u + mx[c][6] * v + mx[c][7] * (u * v);
+        }
+        double det = inv3x3(J, iJ);
+        double G[NF][3][3];
+        JF_UNROLL for (int f = 0; f < NF; f++) {
+            double Hh[3][3];
+            JF_UNROLL for (int c = 0; c < 3; c++) {
+                Hh[0][c] = mu_[f][c][1] + mu_[f][c][4] * v + mu_[f][c][5] * w + mu_[f][c][7] * (v * w);
+                Hh[1][c] = mu_[f][c][2] + mu_[f][c][4] * u + mu_[f][c][6] * w + mu_[f][c][7] * (u * w);
+                Hh[2][c] = mu_[f][c][3] + mu_[f][c][5] * u + mu_[f][c][6] * v + mu_[f][c][7] * (u * v);
+            }
+            JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+                G[f][i][j] = iJ[j][0] * Hh[0][i] + iJ[j][1] * Hh[1][i] + iJ[j][2] * Hh[2][i];
+        }
+        double P[3][3];
+        ok &= pt.eval(elem * 8 + g, G, P);
+        JF_UNROLL for (int i = 0; i < 3; i++) {
+            double t0 = det * (P[i][0] * iJ[0][0] + P[i][1] * iJ[1][0] + P[i][2] * iJ[2][0]);   // coefficient of dN/du
+            double t1 = det * (P[i][0] * iJ[0][1] + P[i][1] * iJ[1][1] + P[i][2] * iJ[2][1]);   // dN/dv
+            double t2 = det * (P[i][0] * iJ[0][2] + P[i][1] * iJ[1][2] + P[i][2] * iJ[2][2]);   // dN/dw
+            Ru[i][0] += t0; Ru[i][1] += t0 * v; Ru[i][2] += t0 * w; Ru[i][3] += t0 * (v * w);
+            Rv[i][0] += t1; Rv[i][1] += t1 * u; Rv[i][2] += t1 * w; Rv[i][3] += t1 * (u * w);
+            Rw[i][0] += t2; Rw[i][1] += t2 * u; Rw[i][2] += t2 * v; Rw[i][3] += t2 * (u * v);
+        }
+    }
+    // f_k[i] = sum over monomials: N_k = 1/8 (1 + a u)(1 + b v)(1 + c w) with node signs (a,b,c):
+    // dN_k/du = 1/8 a (1 + b v + c w + b c v w)  -> contributes a/8 (Ru0 + b Ru1 + c Ru2 + b c Ru3), same for v, w.
+    JF_UNROLL for (int k = 0; k < 8; k++) {
+        const double a = (k == 1 || k == 2 || k == 5 || k == 6) ? 1.0 : -1.0;
+        const double b = (k == 2 || k == 3 || k == 6 || k == 7) ? 1.0 : -1.0;
+        const double c = (k >= 4) ? 1.0 : -1.0;
+        JF_UNROLL for (int i = 0; i < 3; i++) {
+            double r = a * (Ru[i][0] + b * Ru[i][1] + c * Ru[i][2] + (b * c) * Ru[i][3])
+                     + b * (Rv[i][0] + a * Rv[i][1] + c * Rv[i][2] + (a * c) * Rv[i][3])
+                     + c * (Rw[i][0] + a * Rw[i][1] + b * Rw[i][2] + (a * b) * Rw[i][3]);
+            out(k, i, 0.125 * r);
+        }
+    }
+    return ok;
+}
+
+}  // namespace jf

@@ -1,0 +1,98 @@
+// handle.h -- the opaque jfem_handle and the internal entry points shared by the .cu files.
+#pragma once
+#include "common.h"
+
+struct ncclComm;
+
+struct CGScalars {        // lives on the device; read by every CG kernel
+    double rr, pAp, alpha, beta, rr_new, bnorm2, thr, rz, rz_new;
+    int iters, done, max_iter, rel;
+    unsigned int ticket[4];
+};
+
+struct jfem_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int index_base = 1;
+    MeshHost mesh;
+    // options
+    int patch_elems = 256;
+    bool deterministic = true, affine = true;
+    // material
+    int mat_kind = -1;
+    double mat[4] = {0, 0, 0, 0};
+    std::vector<double> mat_per_elem;   // unused when homogeneous
+    // patches
+    bool built = false;
+    double setup_seconds = 0;
+    PatchSetHost hsets[N_CLASSES];
+    InterfaceHost hif;
+    PatchSetDev dsets[N_CLASSES];
+    DevBuf<uint32_t> inodes;
+    DevBuf<int32_t> iptr, islots;
+    DevBuf<double> ipart;
+    DevBuf<double> coords;
+    DevBuf<uint8_t> fixed;              // per dof
+    DevBuf<double> prescribed;          // per dof (values of fixed dofs)
+    int64_t n_fixed = 0;
+    // nonlinear state
+    DevBuf<double> ulin;                // linearisation point
+    bool has_lin = false;
+    DevBuf<double> st_old, st_new;      // 13 x n_gp SoA (internal element order)
+    DevBuf<int> dflags;                 // [0] = fail flag (invalid deformation)
+    // work vectors
+    DevBuf<double> wx, wy;              // staging for host-pointer calls
+    DevBuf<double> cg_r, cg_p, cg_Ap, cg_z, cg_dinv, nk_R, nk_du, nk_f;
+    DevBuf<double> red_partials;
+    DevBuf<CGScalars> cg_s;
+    // CSR
+    bool csr_built = false;
+    std::vector<int64_t> h_nadj_ptr;    // node adjacency (host)
+    std::vector<int32_t> h_nadj;
+    DevBuf<int64_t> nadj_ptr, rowptr;
+    DevBuf<int32_t> nadj, colind;
+    DevBuf<double> vals;
+    DevBuf<uint16_t> eblk;              // per element nnpe x nnpe : position of node l in adjacency of node k
+    DevBuf<int32_t> dconn;              // device connectivity, caller order, 0-based
+    DevBuf<int32_t> colour_elems;       // elements sorted by colour
+    std::vector<int64_t> colour_ptr;
+    DevBuf<int64_t> e2i;                // caller element -> internal element index (state lookup)
+    bool vals_valid = false;
+    // comm
+    ncclComm *comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    int64_t n_owned_nodes = -1;
+    std::vector<int> nb_rank;
+    std::vector<int64_t> send_ptr, recv_ptr;
+    DevBuf<int32_t> send_nodes, recv_nodes;
+    DevBuf<double> send_buf, recv_buf;
+    // stats
+    int64_t matvec_launches = 0, total_launches = 0;
+
+    int64_t n_dofs() const { return 3 * mesh.n_nodes; }
+    int64_t n_owned_dofs() const { return 3 * (n_owned_nodes >= 0 ? n_owned_nodes : mesh.n_nodes); }
+    int ngp() const { return mesh.nnpe == 10 ? 4 : (mesh.nnpe == 8 ? 8 : 1); }
+};
+
+// modes of the element operator
+enum { OP_LINEAR = 0, OP_RESIDUAL = 1, OP_TANGENT = 2 };
+
+int ensure_built(jfem_handle *h);
+int op_apply(jfem_handle *h, int mode, const double *x_dev, double *y_dev, int flags, const int *done_flag);
+int halo_exchange(jfem_handle *h, double *x_dev);
+int comm_allreduce_sum(jfem_handle *h, double *buf_dev, int count);
+int upload_fixed(jfem_handle *h);
+
+int cg_solve(jfem_handle *h, const double *b_dev, double *x_dev, double tol, int rel, int max_iter, int flags, int *iters, double *resid);
+int newton_krylov(jfem_handle *h, const double *fext_dev, double *u_dev, double newton_tol, int max_newton, int max_cg,
+                  double forcing_power, double forcing_max, int flags, int *newton_iters, int *cg_iters, double *resid,
+                  double *history, int history_cap);
+int vec_dot(jfem_handle *h, const double *a, const double *b, double *out_host);
+
+int csr_build(jfem_handle *h);
+int csr_assemble(jfem_handle *h, const double *u_dev, int symmetrise);
+int csr_fint(jfem_handle *h, const double *u_dev, double *f_dev);
+int csr_spmv(jfem_handle *h, const double *x_dev, double *y_dev, int flags, const int *done_flag);
+int element_matrices(jfem_handle *h, const double *u_dev, int64_t e0, int64_t ne, double *Ke_dev, double *fe_dev);
+int jacobi_build(jfem_handle *h, int flags);

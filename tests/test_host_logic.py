@@ -1,0 +1,127 @@
+"""CPU: mesh generators, Abaqus reader, partitioner, C-ABI symbol export.  No GPU, no compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_abi_exports_every_declared_symbol(jf):
+    from juliafem.jl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "jfem_b200.h")).read()
+    declared = set(re.findall(r"\b(jfem_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("jfem_handle")
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/jfem_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.lib().jfem_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure(jf):
+    from juliafem.jl_b200 import _lib
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = jf.mesh.tet10_kuhn(1, 1, 1)
+    with pytest.raises(_lib.JfemError) as ei:
+        _lib.Handle(10, m.coords, m.conn)
+    assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
+
+
+def test_unsupported_element_is_refused(jf):
+    """Mirror of test/test_problems_elasticity_assemble_3d_seg3.jl:7-12 (assemble! throws for Seg3 in 3D)."""
+    from juliafem.jl_b200 import _lib
+    with pytest.raises(_lib.JfemError) as ei:
+        _lib.Handle(3, np.zeros((3, 3)), np.array([[1, 2, 3]], dtype=np.int32))
+    assert ei.value.code == 1 and "unsupported element type" in str(ei.value)
+
+
+def test_hex8_lattice_matches_reference_numbering(jf):
+    m = jf.mesh.hex8_lattice(4, 3, 3)
+    assert m.n_nodes == 36 and m.n_elems == 12
+    nx, ny = 4, 3
+    # benchmarks/multigpu_mpi_benchmark.jl:86-94 for the first element and one interior element
+    assert m.conn[0].tolist() == [1, 2, 2 + nx, 1 + nx, 1 + nx * ny, 2 + nx * ny, 2 + nx + nx * ny, 1 + nx + nx * ny]
+    k, j, i = 1, 1, 2   # 0-based cell indices
+    n1 = k * nx * ny + j * nx + i + 1
+    e = k * (ny - 1) * (nx - 1) + j * (nx - 1) + i
+    assert m.conn[e, 0] == n1 and m.conn[e, 6] == n1 + 1 + nx + nx * ny
+    assert np.allclose(m.coords[n1 - 1], [i, j, k])
+
+
+def test_tet10_kuhn_sizes(jf):
+    # T1 = 88x22x22 cells -> 358 425 nodes, 255 552 elements (checked on a scaled-down box + formula)
+    m = jf.mesh.tet10_kuhn(4, 2, 2)
+    assert m.n_nodes == 9 * 5 * 5 and m.n_elems == 6 * 16
+    assert (2 * 88 + 1) * (2 * 22 + 1) ** 2 == 358425 and 6 * 88 * 22 * 22 == 255552
+    X = m.coords[m.conn - 1]
+    det = np.linalg.det(X[:, 1:4] - X[:, :1])
+    assert np.all(det > 0) and abs(det.sum() / 6 - 1.0 * 0.5 * 0.5) < 1e-12
+    for k, (a, b) in enumerate([(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]):
+        assert np.allclose(X[:, 4 + k], 0.5 * (X[:, a] + X[:, b]))
+
+
+def test_abaqus_reader_roundtrip(tmp_path, jf):
+    m = jf.mesh.tet10_kuhn(1, 1, 1)
+    p = tmp_path / "m.inp"
+    with open(p, "w") as fh:
+        fh.write("*HEADING\n** comment\n*NODE, NSET=ALL\n")
+        for i, c in enumerate(m.coords):
+            fh.write(f"{10 * (i + 1)}, {c[0]}, {c[1]}, {c[2]}\n")
+        fh.write("*ELEMENT, TYPE=C3D10, ELSET=BODY\n")
+        for e, c in enumerate(m.conn):
+            ids = [str(10 * int(n)) for n in c]
+            fh.write(f"{e + 1}, " + ", ".join(ids[:7]) + ",\n" + ", ".join(ids[7:]) + "\n")
+        fh.write("*NSET, NSET=LEFT, GENERATE\n10, 30, 10\n*ELSET, ELSET=FIRST\n1, 2\n")
+    r = jf.mesh.read_abaqus_inp(str(p))
+    assert r.elem_type == 10 and r.n_nodes == m.n_nodes and np.array_equal(r.conn, m.conn)
+    assert np.allclose(r.coords, m.coords)
+    assert r.node_sets["LEFT"].tolist() == [1, 2, 3] and r.elem_sets["FIRST"].tolist() == [1, 2]
+    assert r.elem_sets["BODY"].size == 6
+
+
+def test_fixture_mesh_loads(jf):
+    d = np.load(os.path.join(HERE, "golden", "tet10_fixture.npz"))
+    assert d["coords"].shape == (607, 3) and d["conn"].shape == (269, 10)
+    assert d["conn"].min() == 1 and d["conn"].max() == 607
+
+
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_partition_covers_mesh_and_halo_is_consistent(jf, P):
+    m = jf.mesh.hex8_lattice(5, 4, 7)
+    parts = [jf.mesh.partition_mesh(m, P, r) for r in range(P)]
+    owned = np.concatenate([p.local_nodes[:p.n_owned] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(1, m.n_nodes + 1))
+    for p in parts:
+        lo, hi = p.owned_range
+        assert np.array_equal(p.local_nodes[:p.n_owned], np.arange(lo, hi + 1))
+        gh = p.local_nodes[p.n_owned:]
+        assert np.all(np.diff(gh) > 0) and np.all((gh < lo) | (gh > hi))
+        # every element touching an owned node is local
+        touches = ((m.conn >= lo) & (m.conn <= hi)).any(axis=1)
+        assert np.array_equal(np.nonzero(touches)[0], p.elems)
+        assert np.array_equal(p.local_nodes[p.conn_local - 1], m.conn[p.elems])
+        for s, ids in p.send.items():
+            q = parts[s]
+            assert np.array_equal(p.local_nodes[ids - 1], q.local_nodes[q.recv[p.rank] - 1])
+        for s, ids in p.recv.items():
+            assert np.all(ids > p.n_owned) and np.all(np.diff(ids) == 1)   # contiguous ghost segment per neighbour
+
+
+def test_partitioned_matvec_equals_global(oracle, jf):
+    """Owner-computes with ghost elements reproduces the global K.u on owned rows (oracle arithmetic, CPU)."""
+    m = jf.mesh.tet10_kuhn(3, 2, 2)
+    u = jf.mesh.test_vector(m.n_dofs)
+    y = oracle.matfree(10, m.coords, m.conn, u).reshape(-1, 3)
+    for P in (2, 3):
+        for r in range(P):
+            p = jf.mesh.partition_mesh(m, P, r)
+            ul = u.reshape(-1, 3)[p.local_nodes - 1].ravel()
+            yl = oracle.matfree(10, m.coords[p.local_nodes - 1], p.conn_local, ul).reshape(-1, 3)
+            ref = y[p.local_nodes[:p.n_owned] - 1]
+            assert np.abs(yl[:p.n_owned] - ref).max() < 1e-12 * np.abs(y).max()

@@ -1,0 +1,243 @@
+"""CPU: the oracle against every known-answer value that survives in the reference (tests/golden/pins.json,
+SURVEY.md 8c) and against analytic identities.  No GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PINS = json.load(open(os.path.join(HERE, "golden", "pins.json")))
+
+
+def test_le_uniaxial_pin(oracle):
+    p = PINS["le_uniaxial"]
+    s, D = oracle.le_stress(p["E"], p["nu"], p["eps"])
+    assert abs(s[0] / 1e6 - p["sigma11_MPa"]) < 1e-6
+    assert abs(s[1] / 1e6 - p["sigma22_MPa"]) < 1e-6 and abs(s[2] / 1e6 - p["sigma22_MPa"]) < 1e-6
+
+
+def test_le_pure_shear_pin(oracle):
+    p = PINS["le_pure_shear"]
+    s, _ = oracle.le_stress(p["E"], p["nu"], [0, 0, 0, p["gamma12"] / 2, 0, 0])
+    assert abs(s[3] / 1e6 - p["sigma12_MPa"]) < 5e-3
+
+
+def test_le_tangent_identity(oracle):
+    eps = np.array(PINS["le_tangent_identity"]["eps"])
+    s, D = oracle.le_stress(200e9, 0.3, eps)
+    voigt = eps.copy(); voigt[3:] *= 2.0          # engineering shears
+    assert relerr(D @ voigt, s) < 1e-15
+
+
+def test_pp_uniaxial_pin(oracle):
+    p = PINS["pp_uniaxial"]
+    s, D, st, plastic = oracle.pp_stress([p["E"], p["nu"], p["sigma_y"], p["H"]], [p["eps11"], 0, 0, 0, 0, 0])
+    assert plastic
+    assert abs(s[0] / 1e6 - p["sigma11_MPa"]) < 1e-5
+    assert abs(st[0] - p["eps_p11"]) < 1e-8
+    assert abs(st[6] / 1e6 - p["alpha11_MPa"]) < 1e-5
+    assert abs(st[12] - p["kappa"]) < 1e-8
+
+
+def test_pp_on_yield_surface(oracle):
+    par = [200e9, 0.3, 250e6, 1e9]
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        eps = 4e-3 * rng.standard_normal(6)
+        s, D, st, plastic = oracle.pp_stress(par, eps)
+        if not plastic:
+            continue
+        r = s - st[6:12]
+        r[:3] -= r[:3].mean()
+        q = np.sqrt(1.5 * (np.sum(r[:3] ** 2) + 2 * np.sum(r[3:] ** 2)))
+        assert abs(q / 1e6 - PINS["pp_on_surface"]["sigma_y_MPa"]) < 1e-6
+
+
+def test_pp_elastic_step_keeps_state(oracle):
+    par = [200e9, 0.3, 250e6, 1e9]
+    s, D, st, plastic = oracle.pp_stress(par, [1e-4, 0, 0, 0, 0, 0])
+    assert not plastic and np.all(st == 0)
+    s2, _ = oracle.le_stress(200e9, 0.3, [1e-4, 0, 0, 0, 0, 0])
+    assert relerr(s, s2) < 1e-15
+
+
+def test_quadrature_pins(oracle):
+    q = PINS["quadrature"]
+    w, xi = oracle.quadrature(10)
+    assert len(w) == 4 and np.all(w == q["gltet4_weight"]) and abs(w.sum() - q["tet_volume"]) < 1e-16
+    a, b = (5 + 3 * np.sqrt(5.0)) / 20, (5 - np.sqrt(5.0)) / 20
+    assert np.array_equal(xi, np.array([[a, b, b], [b, a, b], [b, b, a], [b, b, b]]))
+    w, xi = oracle.quadrature(4)
+    assert len(w) == 1 and w[0] == q["gltet1_weight"] and np.all(xi == 0.25)
+    w, xi = oracle.quadrature(8)
+    assert len(w) == 8 and w.sum() == q["hex_volume"] and np.all(np.abs(xi) == q["glhex8_point"])
+    # first index fastest (src/quadrature/glquad.jl:12-15)
+    assert xi[0].tolist() == [-q["glhex8_point"]] * 3 and xi[1, 0] > 0 and xi[1, 1] < 0 and xi[2, 1] > 0 and xi[4, 2] > 0
+
+
+def _gltet15():
+    # degree-5 rule (src/quadrature/gltet.jl GLTET15), used only to integrate N_i N_j (degree 4) for the mass pin
+    s15 = np.sqrt(15.0)
+    a = 0.25
+    b1, b2 = (7 + s15) / 34, (7 - s15) / 34
+    c1, c2 = (13 - 3 * s15) / 34, (13 + 3 * s15) / 34
+    d, f = (5 - s15) / 20, (5 + s15) / 20
+    w1, w2, w3, w4 = 8 / 405, (2665 - 14 * s15) / 226800, (2665 + 14 * s15) / 226800, 5 / 567
+    pts = [(a, a, a), (b1, b1, b1), (b1, b1, c1), (b1, c1, b1), (c1, b1, b1), (b2, b2, b2), (b2, b2, c2), (b2, c2, b2), (c2, b2, b2),
+           (d, d, f), (d, f, d), (f, d, d), (d, f, f), (f, d, f), (f, f, d)]
+    ws = [w1] + [w2] * 4 + [w3] * 4 + [w4] * 6
+    return np.array(ws), np.array(pts)
+
+
+def test_tet10_mass_matrix_pin(oracle):
+    """Pins the Tet10 shape functions AND their node ordering against the integer table of
+    src/assembly/assembly.jl:139-149 (M = detJ/2520 * table for a constant metric)."""
+    table = np.array(PINS["tet10_mass_times_2520"]["table"], dtype=float)
+    w, pts = _gltet15()
+    M = np.zeros((10, 10))
+    for wi, p in zip(w, pts):
+        N = oracle.shape_N(10, p)
+        M += wi * np.outer(N, N)
+    assert np.abs(M * 2520 - table).max() < 1e-11
+
+
+@pytest.mark.parametrize("et", [4, 8, 10])
+def test_partition_of_unity_and_derivative_consistency(oracle, et):
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        xi = rng.random(3) * (0.3 if et != 8 else 1.0)
+        N, dN = oracle.shape_N(et, xi), oracle.shape_dN(et, xi)
+        assert abs(N.sum() - 1) < 1e-14 and np.abs(dN.sum(axis=0)).max() < 1e-14
+        h = 1e-6
+        for a in range(3):
+            e = np.zeros(3); e[a] = h
+            fd = (oracle.shape_N(et, xi + e) - oracle.shape_N(et, xi - e)) / (2 * h)
+            assert np.abs(fd - dN[:, a]).max() < 1e-8
+
+
+def test_nh_closed_form_matches_energy_derivatives(oracle):
+    """S = 2 dpsi/dC and DD = 4 d2psi/dC2 (src/materials/neo_hookean.jl:222) by central differences of strain_energy."""
+    la, mu = oracle.lame(3e6, 0.45)
+    rng = np.random.default_rng(12345)
+    F = np.eye(3) + 0.15 * rng.standard_normal((3, 3))
+    Cm = F.T @ F
+    Em = 0.5 * (Cm - np.eye(3))
+    idx = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]
+    Ev = np.array([Em[i, j] for i, j in idx])
+    S, D = oracle.nh_stress(mu, la, Ev)
+
+    def psi(Cmat):
+        return oracle.nh_energy(mu, la, np.array([Cmat[i, j] for i, j in idx]))
+
+    h = 1e-6
+    for q, (i, j) in enumerate(idx):
+        dC = np.zeros((3, 3)); dC[i, j] += 0.5; dC[j, i] += 0.5
+        dpsi = (psi(Cm + h * dC) - psi(Cm - h * dC)) / (2 * h)
+        assert abs(2 * dpsi - S[q]) < 1e-6 * np.abs(S).max()
+        # tangent: dS = DD : dE, with dE = dC/2
+        Sp, _ = oracle.nh_stress(mu, la, Ev + h * np.array([0.5 * (dC[a, b] + dC[b, a]) / 1 for a, b in idx]) * 0.5 * 2 / 2)
+        Sm, _ = oracle.nh_stress(mu, la, Ev - h * np.array([0.5 * (dC[a, b] + dC[b, a]) / 1 for a, b in idx]) * 0.5 * 2 / 2)
+        dE = 0.5 * np.array([0.5 * (dC[a, b] + dC[b, a]) for a, b in idx])       # tensor components of dE = dC/2
+        voigt = dE.copy(); voigt[3:] *= 2.0
+        assert np.abs((Sp - Sm) / (2 * h) - D @ voigt).max() < 1e-5 * np.abs(D).max() * np.abs(voigt).max()
+    # S(E=0) = 0 and small-strain limit = Hooke (docs/book/neo_hookean_implementation.md:249-259)
+    S0, D0 = oracle.nh_stress(mu, la, np.zeros(6))
+    assert np.abs(S0).max() == 0.0
+    _, Dle = oracle.le_stress(3e6, 0.45, np.zeros(6))
+    assert relerr(D0, Dle) < 1e-14
+    with pytest.raises(ValueError):
+        oracle.nh_stress(mu, la, np.array([-0.6, 0, 0, 0, 0, 0]))   # C11 = -0.2 -> det <= 0
+
+
+def _random_curved_tet10(rng):
+    ref = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [.5, 0, 0], [.5, .5, 0], [0, .5, 0], [0, 0, .5], [.5, 0, .5], [0, .5, .5]], float)
+    A = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+    return ref @ A.T + 0.02 * rng.standard_normal((10, 3))
+
+
+def test_element_stiffness_identities(oracle):
+    """Ke symmetric, 6 rigid-body modes, Voigt form == block form (src/physics/assembly_helpers.jl:218)."""
+    rng = np.random.default_rng(12345)
+    X = _random_curved_tet10(rng)
+    Km, Kg, f, _ = oracle.element(10, X)
+    assert relerr(Km, Km.T) < 1e-14
+    ev = np.linalg.eigvalsh(Km)
+    assert np.sum(np.abs(ev) < 1e-12 * ev[-1]) == 6 and ev[6] > 1e-4 * ev[-1]
+    assert relerr(oracle.element_block_form(10, X, 210e9, 0.3), Km) < 1e-14
+    # infinitesimal rigid rotation
+    W = np.array([[0, -1, 2], [1, 0, -3], [-2, 3, 0]], float) * 1e-3
+    u = (X @ W.T).ravel()
+    assert np.abs(Km @ u).max() < 1e-12 * np.abs(Km).max() * np.abs(u).max()
+    # f_int = Km u for small strain LE
+    _, _, f, _ = oracle.element(10, X, u=rng.standard_normal((10, 3)) * 1e-3)
+
+
+def test_patch_test_linear_field(oracle, jf):
+    """Linear displacement => constant strain => nodal forces vanish at interior nodes."""
+    m = jf.mesh.tet10_kuhn(2, 2, 2)
+    G = np.array([[1e-3, 2e-4, 0], [0, -5e-4, 3e-4], [1e-4, 0, 7e-4]])
+    u = (m.coords @ G.T).ravel()
+    y = oracle.matfree(10, m.coords, m.conn, u).reshape(-1, 3)
+    interior = np.all((m.coords > 1e-9) & (m.coords < 1 - 1e-9), axis=1)
+    assert interior.sum() > 0
+    assert np.abs(y[interior]).max() < 1e-10 * np.abs(y).max()
+    assert np.abs(y.sum(axis=0)).max() < 1e-9 * np.abs(y).max()
+
+
+def test_csr_pattern_is_union_of_element_dof_products(oracle, jf):
+    m = jf.mesh.tet10_kuhn(2, 1, 1)
+    rowptr, colind = oracle.csr_pattern(10, m.n_nodes, m.conn)
+    ref = [set() for _ in range(m.n_dofs)]
+    for e in range(m.n_elems):
+        g = [3 * (n - 1) + c for n in m.conn[e] for c in range(3)]     # src/assembly/problems.jl:476 (0-based)
+        for r in g:
+            ref[r].update(g)
+    for r in range(m.n_dofs):
+        assert colind[rowptr[r]:rowptr[r + 1]].tolist() == sorted(ref[r])
+
+
+def test_assembled_equals_matrix_free_and_scipy(oracle, jf):
+    import scipy.sparse as sp
+    m = jf.mesh.tet10_kuhn(3, 2, 2)
+    rowptr, colind, vals, f = oracle.assemble_csr(10, m.coords, m.conn)
+    u = jf.mesh.test_vector(m.n_dofs)
+    assert relerr(oracle.spmv(rowptr, colind, vals, u), oracle.matfree(10, m.coords, m.conn, u)) < 1e-13
+    # independent COO -> CSR through scipy (stand-in for Julia's sparse(I,J,V))
+    I, J, V = [], [], []
+    for e in range(m.n_elems):
+        Ke, _, _, _ = oracle.element(10, m.coords[m.conn[e] - 1])
+        g = np.array([3 * (n - 1) + c for n in m.conn[e] for c in range(3)])
+        I.append(np.repeat(g, 30)); J.append(np.tile(g, 30)); V.append(Ke.ravel())
+    K = sp.coo_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=(m.n_dofs, m.n_dofs)).tocsr()
+    K.sort_indices()
+    assert np.array_equal(K.indptr, rowptr) and np.array_equal(K.indices, colind)
+    assert relerr(K.data, vals) < 1e-13
+
+
+def test_cg_solves_cantilever(oracle, jf):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m = jf.mesh.tet10_kuhn(4, 1, 1, 4.0, 1.0, 1.0)
+    fixed = jf.mesh.clamp_dofs(m)
+    rowptr, colind, vals, _ = oracle.assemble_csr(10, m.coords, m.conn, par=(210e9, 0.3))
+    b = np.zeros(m.n_dofs); b[2::3] = -1e3
+    x, it, res = oracle.cg_csr(rowptr, colind, vals, b, fixed_dofs=fixed, tol=1e-10, relative=True, max_iter=5000)
+    assert it < 5000
+    K = sp.csr_matrix((vals, colind, rowptr))
+    free = np.setdiff1d(np.arange(m.n_dofs), fixed - 1)
+    xd = np.zeros(m.n_dofs)
+    xd[free] = spla.spsolve(K[free][:, free].tocsc(), b[free])     # elimination solve (src/solvers.jl:205-210)
+    assert relerr(x, xd) < 1e-6
+    assert np.all(x[fixed - 1] == 0)
+
+
+def test_colouring_is_valid(oracle, jf):
+    m = jf.mesh.tet10_kuhn(3, 3, 3)
+    col, n = oracle.colouring(10, m.n_nodes, m.conn)
+    assert n >= 24
+    for c in range(n):
+        nodes = m.conn[col == c].ravel()
+        assert nodes.size == np.unique(nodes).size
