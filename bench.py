@@ -270,7 +270,7 @@ def main():
             "config": {"workload": f"{args.workload}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {total_dofs} DOF, {m.n_elems} elements, "
                                    f"linear elastic E=210e9 nu=0.3, clamp x=0, deterministic scatter",
                        "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
-                       "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems),
+                       "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems), "smem_bytes": int(info.smem_bytes), "blocks_per_sm": int(info.blocks_per_sm), "interface_nodes": int(info.n_interface_nodes),
                        "partition": "z-slabs by contiguous node range, owner-computes + ghost elements" if world > 1 else "single GPU",
                        "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds)},
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,

@@ -68,6 +68,8 @@ typedef struct jfem_info {
     int64_t device_bytes;        /* device memory held by the handle */
     int64_t matvec_launches;     /* kernel launches issued by the last jfem_matvec */
     int64_t total_launches;      /* kernel launches issued since creation */
+    int64_t smem_bytes;          /* dynamic shared memory per block of the last patch kernel */
+    int64_t blocks_per_sm;       /* resident blocks per SM of the last patch kernel */
     double setup_seconds;        /* host time spent building patches */
 } jfem_info;
 

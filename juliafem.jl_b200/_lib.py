@@ -43,7 +43,8 @@ class Info(C.Structure):
                 ("n_nodes", C.c_int64), ("n_elems", C.c_int64), ("n_dofs", C.c_int64), ("n_fixed", C.c_int64),
                 ("n_patches", C.c_int64), ("n_interface_nodes", C.c_int64), ("n_affine_elems", C.c_int64),
                 ("patch_elems", C.c_int64), ("patch_max_nodes", C.c_int64), ("device_bytes", C.c_int64),
-                ("matvec_launches", C.c_int64), ("total_launches", C.c_int64), ("setup_seconds", C.c_double)]
+                ("matvec_launches", C.c_int64), ("total_launches", C.c_int64), ("smem_bytes", C.c_int64),
+                ("blocks_per_sm", C.c_int64), ("setup_seconds", C.c_double)]
 
 
 _lib = None

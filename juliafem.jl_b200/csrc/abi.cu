@@ -81,7 +81,7 @@ int jfem_create(jfem_handle **out, int device, int elem_type, int64_t n_nodes, i
     if (prop.major != 10) { jfem_set_error("device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor); return JFEM_ENODEV; }
     JFEM_CUDA(cudaSetDevice(device));
     jfem_handle *h = new jfem_handle();
-    h->device = device; h->index_base = index_base;
+    h->device = device; h->index_base = index_base; h->n_sms = prop.multiProcessorCount;
     h->mesh.nnpe = elem_type; h->mesh.n_nodes = n_nodes; h->mesh.n_elems = n_elems;
     h->mesh.coords.assign(coords, coords + 3 * n_nodes);
     h->mesh.conn.resize((size_t)n_elems * elem_type);
@@ -104,7 +104,7 @@ int jfem_destroy(jfem_handle *h) {
     cudaStreamSynchronize(h->stream);
     jfem_comm_destroy(h);
     for (int c = 0; c < N_CLASSES; c++) h->dsets[c].release();
-    h->inodes.release(); h->iptr.release(); h->islots.release(); h->ipart.release(); h->coords.release(); h->fixed.release();
+    h->inodes.release(); h->iptr.release(); h->islots.release(); h->islot4.release(); h->ipart.release(); h->coords.release(); h->fixed.release();
     h->prescribed.release(); h->ulin.release(); h->st_old.release(); h->st_new.release(); h->dflags.release(); h->wx.release(); h->wy.release();
     h->cg_r.release(); h->cg_p.release(); h->cg_Ap.release(); h->cg_z.release(); h->cg_dinv.release(); h->nk_R.release(); h->nk_du.release();
     h->nk_f.release(); h->red_partials.release(); h->cg_s.release(); h->nadj_ptr.release(); h->rowptr.release(); h->nadj.release();
@@ -122,6 +122,9 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         int v = (int)value;
         if (v != 128 && v != 256 && v != 512) { jfem_set_error("patch_elems must be 128, 256 or 512"); return JFEM_EINVAL; }
         if (v != h->patch_elems) { h->patch_elems = v; h->built = false; }
+    } else if (!strcmp(key, "debug_timing")) {
+        if (value != 0) { JFEM_TRY(h->timing.alloc(64)); JFEM_CUDA(cudaMemset(h->timing.p, 0, 64 * sizeof(long long))); }
+        else h->timing.release();
     } else if (!strcmp(key, "deterministic")) {
         h->deterministic = value != 0;
     } else if (!strcmp(key, "affine_fast_path")) {
@@ -192,6 +195,7 @@ int jfem_get_info(jfem_handle *h, jfem_info *info) {
                                         h->vals.bytes() + h->eblk.bytes() + h->nadj.bytes() + h->nadj_ptr.bytes() + h->dconn.bytes() + h->e2i.bytes());
     }
     info->matvec_launches = h->matvec_launches; info->total_launches = h->total_launches; info->setup_seconds = h->setup_seconds;
+    info->smem_bytes = h->last_smem; info->blocks_per_sm = h->last_blocks_per_sm;
     return JFEM_OK;
 }
 
@@ -206,6 +210,14 @@ int jfem_set_stream(jfem_handle *h, void *cuda_stream) {
 int jfem_synchronize(jfem_handle *h) {
     CHECK_H(h);
     JFEM_CUDA(cudaStreamSynchronize(h->stream));
+    return JFEM_OK;
+}
+
+int jfem_debug_timing(jfem_handle *h, long long *out64) {   /* not part of the public header: debugging aid */
+    CHECK_H(h);
+    if (!h->timing.p) { jfem_set_error("debug_timing option is off"); return JFEM_ESTATE; }
+    JFEM_CUDA(cudaStreamSynchronize(h->stream));
+    JFEM_CUDA(cudaMemcpy(out64, h->timing.p, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     return JFEM_OK;
 }
 

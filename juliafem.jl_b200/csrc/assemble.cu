@@ -64,14 +64,15 @@ __global__ void __launch_bounds__(128) elem_columns_kernel(AsmArgs a, Pt pt) {
         double *vals = a.vals;
         const long long *adjptr = a.adjptr;
         const uint16_t *blk = a.eblk + e * NNPE * NNPE;
-        auto out = [=](int k, int c, double v) {
+        auto out = [=](int k, double v0, double v1, double v2) {
             const long long ap = adjptr[n[k]], deg = adjptr[n[k] + 1] - ap;
-            vals[9 * ap + 3 * c * deg + 3 * blk[k * NNPE + kj] + cj] += v;
+            double *d = vals + 9 * ap + 3 * blk[k * NNPE + kj] + cj;
+            d[0] += v0; d[3 * deg] += v1; d[6 * deg] += v2;
         };
         ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
     } else {
         double *Ke = a.Ke + (i * ND + j) * ND;
-        auto out = [=](int k, int c, double v) { Ke[3 * k + c] = v; };
+        auto out = [=](int k, double v0, double v1, double v2) { Ke[3 * k] = v0; Ke[3 * k + 1] = v1; Ke[3 * k + 2] = v2; };
         ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
     }
     if (!ok) atomicOr(a.fail, 1);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(128) elem_fint_kernel(AsmArgs a, Pt pt, double
     AField X{a.coords, n, 0, 0};
     AField F[1] = {AField{a.u, n, 0, 0}};
     double *o = fe + i * ND;
-    auto out = [=](int k, int c, double v) { o[3 * k + c] = v; };
+    auto out = [=](int k, double v0, double v1, double v2) { o[3 * k] = v0; o[3 * k + 1] = v1; o[3 * k + 2] = v2; };
     bool ok = elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
     if (!ok) atomicOr(a.fail, 1);
 }

@@ -78,21 +78,23 @@ struct PatchSetHost {
     std::vector<int32_t> ipart_base;   // per patch: first interface-partial slot (in nodes)
     std::vector<uint16_t> lconn;       // [(p*nnpe+k)*EP + t] local node index (0xFFFF = no element)
     std::vector<uint16_t> goff;        // per patch Np+1 offsets, at pnode_ptr[p]+p
-    std::vector<uint16_t> gslots;      // per patch at p*EP*nnpe : slot = 3*k*EP + t
+    std::vector<uint16_t> gslots;      // per patch [k*EP + t]: position of element t's node k in the node-major staging tile
+    std::vector<uint16_t> xslot;       // per patch node: slot in the compact coordinate tile (0xFFFF: coordinates not needed)
+    int max_nx = 0;                    // max #nodes per patch whose coordinates are needed
+    // everything above packed per patch into one 16-byte aligned blob (what the kernel streams in by TMA bulk copy):
+    //   [0,16) header {np, n_iface | nx<<16, ipart_base, n_elems} | pnodes u32[max_nodes] | xlist u32[max_nx] (ids of the nodes
+    //   whose coordinates are needed) | xslot u16[max_nodes] | goff u16[max_nodes+1] | rank u8[nnpe*EP] | lconn u16[nnpe*EP]
+    std::vector<uint8_t> blob;
+    int off_pn = 0, off_xl = 0, off_xs = 0, off_go = 0, off_gs = 0, off_lc = 0, stride = 0;
 };
 
 struct PatchSetDev {
     int cls = 0, nnpe = 0, EP = 0, n_patches = 0, max_nodes = 0;
     int64_t n_elems = 0, elem_offset = 0;  // offset of this set in the internal element order
-    DevBuf<int32_t> pnode_ptr, n_iface, ipart_base;
-    DevBuf<uint32_t> pnodes;
-    DevBuf<uint16_t> lconn, goff, gslots;
-    size_t bytes() const {
-        return pnode_ptr.bytes() + n_iface.bytes() + ipart_base.bytes() + pnodes.bytes() + lconn.bytes() + goff.bytes() + gslots.bytes();
-    }
-    void release() {
-        pnode_ptr.release(); n_iface.release(); ipart_base.release(); pnodes.release(); lconn.release(); goff.release(); gslots.release();
-    }
+    int max_nx = 0, off_pn = 0, off_xl = 0, off_xs = 0, off_go = 0, off_gs = 0, off_lc = 0, stride = 0;
+    DevBuf<uint8_t> blob;
+    size_t bytes() const { return blob.bytes(); }
+    void release() { blob.release(); }
 };
 
 struct InterfaceHost {

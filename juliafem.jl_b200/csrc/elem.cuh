@@ -199,7 +199,7 @@ struct PtPPTangent : PPCommon {   // field 0 = v, field 1 = u;  dP = DD_ep : sym
 
 // ------------------------------------------------------------------------------------------------
 // Tet10, isoparametric (valid for curved elements), GLTET4.  F[f] are the NF fields to differentiate,
-// X the coordinates; out(k, c, value) receives the element vector.  Returns false on invalid deformation.
+// X the coordinates; out(k, v0, v1, v2) receives the 3 components of node k of the element vector.  Returns false on invalid deformation.
 // ------------------------------------------------------------------------------------------------
 template <class Pt, class FLD, class OUT>
 __device__ __forceinline__ bool tet10_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
@@ -252,9 +252,11 @@ __device__ __forceinline__ bool tet10_general(const Pt &pt, long long elem, cons
             JF_UNROLL for (int i = 0; i < 3; i++) fo[e][i] = first ? k4 * T[a][i] : fo[e][i] + k4 * T[a][i];
         }
     }
-    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int i = 0; i < 3; i++) out(a, i, fo[a][i] + c1 * ST[a][i]);
-    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int b = a + 1; b < 4; b++) JF_UNROLL for (int i = 0; i < 3; i++)
-        out(t10_edge(a, b), i, fo[t10_edge(a, b)][i] + c4b * (ST[a][i] + ST[b][i]));
+    JF_UNROLL for (int a = 0; a < 4; a++) out(a, fo[a][0] + c1 * ST[a][0], fo[a][1] + c1 * ST[a][1], fo[a][2] + c1 * ST[a][2]);
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int b = a + 1; b < 4; b++) {
+        const int e = t10_edge(a, b);
+        out(e, fo[e][0] + c4b * (ST[a][0] + ST[b][0]), fo[e][1] + c4b * (ST[a][1] + ST[b][1]), fo[e][2] + c4b * (ST[a][2] + ST[b][2]));
+    }
     return ok;
 }
 
@@ -305,7 +307,7 @@ __device__ __forceinline__ void tet10_affine_linear(double la, double mu, const 
         double m[6], r[3];
         JF_UNROLL for (int q = 0; q < 6; q++) m[q] = v20 * (4.0 * sg[a][q] - S[q]);
         mulsym(m, g[a], r);
-        JF_UNROLL for (int i = 0; i < 3; i++) out(a, i, r[i]);
+        out(a, r[0], r[1], r[2]);
     }
     double Q[4][6];
     JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int q = 0; q < 6; q++) Q[a][q] = v5 * (S[q] + sg[a][q]);
@@ -313,7 +315,7 @@ __device__ __forceinline__ void tet10_affine_linear(double la, double mu, const 
         double r1[3], r2[3];
         mulsym(Q[b], g[a], r1);
         mulsym(Q[a], g[b], r2);
-        JF_UNROLL for (int i = 0; i < 3; i++) out(t10_edge(a, b), i, r1[i] + r2[i]);
+        out(t10_edge(a, b), r1[0] + r2[0], r1[1] + r2[1], r1[2] + r2[2]);
     }
 }
 
@@ -336,12 +338,14 @@ __device__ __forceinline__ bool tet4_general(const Pt &pt, long long elem, const
     double P[3][3];
     bool ok = pt.eval(elem, G, P);
     double w = det * (1.0 / 6.0);
+    double t[4][3];
     JF_UNROLL for (int i = 0; i < 3; i++) {
-        double t1 = w * (P[i][0] * iJ[0][0] + P[i][1] * iJ[1][0] + P[i][2] * iJ[2][0]);
-        double t2 = w * (P[i][0] * iJ[0][1] + P[i][1] * iJ[1][1] + P[i][2] * iJ[2][1]);
-        double t3 = w * (P[i][0] * iJ[0][2] + P[i][1] * iJ[1][2] + P[i][2] * iJ[2][2]);
-        out(0, i, -(t1 + t2 + t3)); out(1, i, t1); out(2, i, t2); out(3, i, t3);
+        t[1][i] = w * (P[i][0] * iJ[0][0] + P[i][1] * iJ[1][0] + P[i][2] * iJ[2][0]);
+        t[2][i] = w * (P[i][0] * iJ[0][1] + P[i][1] * iJ[1][1] + P[i][2] * iJ[2][1]);
+        t[3][i] = w * (P[i][0] * iJ[0][2] + P[i][1] * iJ[1][2] + P[i][2] * iJ[2][2]);
+        t[0][i] = -(t[1][i] + t[2][i] + t[3][i]);
     }
+    JF_UNROLL for (int k = 0; k < 4; k++) out(k, t[k][0], t[k][1], t[k][2]);
     return ok;
 }
 
@@ -418,12 +422,12 @@ __device__ __forceinline__ bool hex8_general(const Pt &pt, long long elem, const
         const double a = (k == 1 || k == 2 || k == 5 || k == 6) ? 1.0 : -1.0;
         const double b = (k == 2 || k == 3 || k == 6 || k == 7) ? 1.0 : -1.0;
         const double c = (k >= 4) ? 1.0 : -1.0;
-        JF_UNROLL for (int i = 0; i < 3; i++) {
-            double r = a * (Ru[i][0] + b * Ru[i][1] + c * Ru[i][2] + (b * c) * Ru[i][3])
-                     + b * (Rv[i][0] + a * Rv[i][1] + c * Rv[i][2] + (a * c) * Rv[i][3])
-                     + c * (Rw[i][0] + a * Rw[i][1] + b * Rw[i][2] + (a * b) * Rw[i][3]);
-            out(k, i, 0.125 * r);
-        }
+        double r[3];
+        JF_UNROLL for (int i = 0; i < 3; i++)
+            r[i] = 0.125 * (a * (Ru[i][0] + b * Ru[i][1] + c * Ru[i][2] + (b * c) * Ru[i][3])
+                          + b * (Rv[i][0] + a * Rv[i][1] + c * Rv[i][2] + (a * c) * Rv[i][3])
+                          + c * (Rw[i][0] + a * Rw[i][1] + b * Rw[i][2] + (a * b) * Rw[i][3]));
+        out(k, r[0], r[1], r[2]);
     }
     return ok;
 }

@@ -11,7 +11,7 @@ struct CGScalars {        // lives on the device; read by every CG kernel
 };
 
 struct jfem_handle {
-    int device = 0;
+    int device = 0, n_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int index_base = 1;
@@ -30,7 +30,7 @@ struct jfem_handle {
     InterfaceHost hif;
     PatchSetDev dsets[N_CLASSES];
     DevBuf<uint32_t> inodes;
-    DevBuf<int32_t> iptr, islots;
+    DevBuf<int32_t> iptr, islots, islot4;
     DevBuf<double> ipart;
     DevBuf<double> coords;
     DevBuf<uint8_t> fixed;              // per dof
@@ -40,6 +40,7 @@ struct jfem_handle {
     DevBuf<double> ulin;                // linearisation point
     bool has_lin = false;
     DevBuf<double> st_old, st_new;      // 13 x n_gp SoA (internal element order)
+    DevBuf<long long> timing;           // debug phase timing (option "debug_timing")
     DevBuf<int> dflags;                 // [0] = fail flag (invalid deformation)
     // work vectors
     DevBuf<double> wx, wy;              // staging for host-pointer calls
@@ -68,7 +69,7 @@ struct jfem_handle {
     DevBuf<int32_t> send_nodes, recv_nodes;
     DevBuf<double> send_buf, recv_buf;
     // stats
-    int64_t matvec_launches = 0, total_launches = 0;
+    int64_t matvec_launches = 0, total_launches = 0, last_smem = 0, last_blocks_per_sm = 0;
 
     int64_t n_dofs() const { return 3 * mesh.n_nodes; }
     int64_t n_owned_dofs() const { return 3 * (n_owned_nodes >= 0 ? n_owned_nodes : mesh.n_nodes); }

@@ -17,111 +17,239 @@
 using namespace jf;
 
 struct PatchKArgs {
-    const int32_t *pnode_ptr;
-    const uint32_t *pnodes;
-    const int32_t *n_iface;
-    const int32_t *ipart_base;
-    const uint16_t *lconn;
-    const uint16_t *goff;
-    const uint16_t *gslots;
+    const uint8_t *blob;       // n_patches x stride bytes
+    int n_patches, stride, off_pn, off_xl, off_xs, off_go, off_gs, off_lc;
+    int max_nodes, max_nx;
     const double *coords;
     const double *x;
     const double *ulin;
     double *y;
     double *ipart;
-    long long n_elems, elem_offset;
-    int max_nodes, project, atomic_iface;
+    long long elem_offset;
+    int project, atomic_iface, group_smem;
     int *fail;
     const int *done;
+    long long *timing;         // debug: per-phase clock64 stamps of block 0 (nullptr = off)
 };
 
-template <int NNPE, int CLS, int MODE, class Pt, int T>
-__global__ void __launch_bounds__(T) patch_kernel(PatchKArgs a, Pt pt) {
-    extern __shared__ double sm[];
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Persistent kernel: block b processes patches b, b+grid, b+2*grid, ...   Software pipeline per patch:
+//   (a) wait for x / coordinates of the patch nodes: gathered asynchronously (cp.async) into shared memory during the
+//       previous patch's phase 2, when the xs/Xs tiles are already free
+//   (b) barrier; one thread issues the TMA bulk copy of the metadata blob of the patch after this one
+//   (c) phase 1: one thread per element, register-resident contraction (elem.cuh); the 3*nnpe results are written
+//       to a node-major staging tile (all contributions to one node contiguous, one plane per component)
+//   (d) barrier; wait for the next blob; issue the asynchronous gather of the NEXT patch's x / coordinates
+//   (e) phase 2: one thread per node: sum the node's contiguous run in fixed order (deterministic, no atomics);
+//       interior nodes -> y, interface nodes -> one partial slot per (patch, node) for iface_reduce_kernel.
+// Gathers and stores use the flat index i = 3*node + component so that a warp touches consecutive addresses wherever
+// consecutive patch nodes have consecutive ids (the patch node lists are id-sorted).
+
+// Ping-pong: a block holds G = 2 independent groups of T threads (when registers allow), each working on its own
+// patch stream with its own shared-memory tiles.  Named barriers force the two groups to take turns in the fp64-bound
+// phase 1, so that one group's gather / reduction / store phases always overlap the other group's arithmetic
+// (two free-running blocks per SM were observed to run in lock-step instead: both in phase 1, then both in phase 2).
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Asynchronous gather (LDGSTS) of the x / coordinate / linearisation-point entries of the patch whose blob is at bl,
+// straight into the shared tiles; no registers are held while the loads are in flight.  Flat index i = 3*node + component.
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int T, int NF>
+__device__ __forceinline__ void patch_gather_async(const PatchKArgs &a, const unsigned char *bl, int tid, double *xs, double *Xs, double *us) {
+    const int *hdr = reinterpret_cast<const int *>(bl);
+    const int n3 = 3 * hdr[0], nx3 = 3 * (int)((unsigned)hdr[1] >> 16);
+    const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+    const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
+    for (int i = tid; i < n3; i += T) {
+        const int j = i / 3;
+        const long long g = 3 * (long long)(pn[j] & PN_ID_MASK) + (i - 3 * j);
+        cp_async8(xs + i, a.x + g);
+        if (NF == 2) cp_async8(us + i, a.ulin + g);
+    }
+    for (int i = tid; i < nx3; i += T) {
+        const int j = i / 3;
+        cp_async8(Xs + i, a.coords + 3 * (long long)xl[j] + (i - 3 * j));
+    }
+    cp_async_commit();
+}
+
+template <int NNPE, int CLS, int MODE>
+struct PatchCfg {
+    static constexpr bool fast = (CLS == CLASS_AFFINE && MODE == OP_LINEAR && NNPE == 10) || NNPE == 4;
+};
+
+template <int NNPE, int CLS, int MODE, class Pt, int T, int G>
+__global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
+    extern __shared__ __align__(128) unsigned char smraw_all[];
     if (a.done && *a.done) return;
     constexpr int NF = Pt::NF;
-    const int p = blockIdx.x, tid = threadIdx.x;
-    const int nb = a.pnode_ptr[p], np = a.pnode_ptr[p + 1] - nb;
-    double *stage = sm;
-    double *xs = sm + 3 * NNPE * T;
+    constexpr int PS = NNPE * T + 5;   // plane stride of the staging tile (odd offset: the 3 planes fall in different banks)
+    const int grp = threadIdx.x / T, tid = threadIdx.x - grp * T;
+    unsigned char *smraw = smraw_all + (size_t)grp * a.group_smem;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smraw);
+    unsigned char *blob0 = smraw + 16;
+    double *stage = reinterpret_cast<double *>(smraw + 16 + 2 * (size_t)a.stride);
+    double *xs = stage + 3 * PS + 1;
     double *Xs = xs + 3 * a.max_nodes;
-    double *us = Xs + 3 * a.max_nodes;
+    double *us = Xs + 3 * a.max_nx;
+    const int stride_p = gridDim.x * G;   // patches are dealt round-robin over blocks first (balanced per SM), then groups
 
-    // ---- phase 0: gather
-    for (int j = tid; j < np; j += T) {
-        const uint32_t w = a.pnodes[nb + j];
-        const long long id = w & PN_ID_MASK;
-        const double *px = a.x + 3 * id;
-        xs[3 * j + 0] = __ldg(px); xs[3 * j + 1] = __ldg(px + 1); xs[3 * j + 2] = __ldg(px + 2);
-        if (w & PN_NEEDX) {
-            const double *pc = a.coords + 3 * id;
-            Xs[3 * j + 0] = __ldg(pc); Xs[3 * j + 1] = __ldg(pc + 1); Xs[3 * j + 2] = __ldg(pc + 2);
-        }
-        if (NF == 2) {
-            const double *pu = a.ulin + 3 * id;
-            us[3 * j + 0] = __ldg(pu); us[3 * j + 1] = __ldg(pu + 1); us[3 * j + 2] = __ldg(pu + 2);
-        }
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
     }
     __syncthreads();
-
-    // ---- phase 1: element contraction
-    const long long el = (long long)p * T + tid;
-    if (el < a.n_elems) {
-        int n[NNPE];
-        JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = a.lconn[((size_t)p * NNPE + k) * T + tid];
-        double *st = stage + tid;
-        auto out = [st](int k, int c, double v) { st[(3 * k + c) * T] = v; };
-        SField X{Xs, n};
-        bool ok = true;
-        if (CLS == CLASS_AFFINE && MODE == OP_LINEAR && NNPE == 10) {
-            SField U{xs, n};
-            tet10_affine_linear(pt.la, pt.mu, U, X, out);
-        } else {
-            SField F[NF];
-            F[0].base = xs; F[0].n = n;
-            if (NF == 2) { F[NF - 1].base = us; F[NF - 1].n = n; }
-            if (NNPE == 10) ok = tet10_general(pt, a.elem_offset + el, F, X, out);
-            else if (NNPE == 8) ok = hex8_general(pt, a.elem_offset + el, F, X, out);
-            else ok = tet4_general(pt, a.elem_offset + el, F, X, out);
-        }
-        if (!ok) atomicOr(a.fail, 1);
+    if (G == 2 && grp == 1) named_arrive(3, 2 * T);   // group 0 takes the first turn in phase 1
+    int p = blockIdx.x + grp * gridDim.x;
+    if (tid == 0 && p < a.n_patches) {
+        mbar_expect_tx(&mbar[0], a.stride);
+        bulk_g2s(blob0, a.blob + (size_t)p * a.stride, a.stride, &mbar[0]);
     }
-    __syncthreads();
+    if (p < a.n_patches) {
+        mbar_wait(&mbar[0], 0);
+        patch_gather_async<T, NF>(a, blob0, tid, xs, Xs, us);
+    }
+    for (int it = 0; p < a.n_patches; it++, p += stride_p) {
+        const int buf = it & 1;
+        const unsigned char *bl = blob0 + (size_t)buf * a.stride;
+        const int *hdr = reinterpret_cast<const int *>(bl);
+        const int np = hdr[0], nif = hdr[1] & 0xFFFF, nx = (int)((unsigned)hdr[1] >> 16), ipb = hdr[2], ne = hdr[3];
+        const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+        const uint16_t *xsl = reinterpret_cast<const uint16_t *>(bl + a.off_xs);
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 0] = clock64();
 
-    // ---- phase 2: per-node ordered reduction
-    const uint16_t *go = a.goff + nb + p;
-    const uint16_t *gs = a.gslots + (size_t)p * T * NNPE;
-    const int nif = a.n_iface[p];
-    for (int j = tid; j < np; j += T) {
-        const int q0 = go[j], q1 = go[j + 1];
-        double s0 = 0, s1 = 0, s2 = 0;
-        for (int q = q0; q < q1; q++) {
-            const int sl = gs[q];
-            s0 += stage[sl]; s1 += stage[sl + T]; s2 += stage[sl + 2 * T];
+        // ---- (a) the asynchronous gather of this patch (issued during the previous patch's phase 2) must have landed
+        cp_async_wait_all();
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 1] = clock64();
+        if (G == 1) __syncthreads(); else named_sync(1 + grp, T);
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 2] = clock64();
+        // ---- (b) every thread has left phase 2 of the previous patch: its blob buffer may be refilled
+        const bool has_next = p + stride_p < a.n_patches;
+        if (tid == 0 && has_next) {
+            mbar_expect_tx(&mbar[buf ^ 1], a.stride);
+            bulk_g2s(blob0 + (size_t)(buf ^ 1) * a.stride, a.blob + (size_t)(p + stride_p) * a.stride, a.stride, &mbar[buf ^ 1]);
         }
-        const uint32_t w = a.pnodes[nb + j];
-        if (a.project) {
-            if (w & (1u << PN_FIXSHIFT)) s0 = 0.0;
-            if (w & (2u << PN_FIXSHIFT)) s1 = 0.0;
-            if (w & (4u << PN_FIXSHIFT)) s2 = 0.0;
-        }
-        if (j < nif) {
-            if (a.atomic_iface) {
-                double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
-                atomicAdd(py, s0); atomicAdd(py + 1, s1); atomicAdd(py + 2, s2);
+
+        // ---- (c) phase 1: element contraction (the two groups alternate here)
+        if (G == 2) named_sync(3 + grp, 2 * T);
+        const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
+        if (tid < ne) {
+            const uint16_t *lc = reinterpret_cast<const uint16_t *>(bl + a.off_lc);
+            const uint8_t *rk = reinterpret_cast<const uint8_t *>(bl + a.off_gs);
+            int n[NNPE];
+            JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = lc[k * T + tid];
+            auto out = [=](int k, double v0, double v1, double v2) {
+                double *d = stage + go[n[k]] + rk[k * T + tid];
+                d[0] = v0; d[PS] = v1; d[2 * PS] = v2;
+            };
+            bool ok = true;
+            const long long el = a.elem_offset + (long long)p * T + tid;
+            if (CLS == CLASS_AFFINE && MODE == OP_LINEAR && NNPE == 10) {
+                int nxs[4];
+                JF_UNROLL for (int k = 0; k < 4; k++) nxs[k] = xsl[n[k]];
+                SField U{xs, n};
+                SField X{Xs, nxs};
+                tet10_affine_linear(pt.la, pt.mu, U, X, out);
             } else {
-                double *pp = a.ipart + 3 * ((long long)a.ipart_base[p] + j);
-                pp[0] = s0; pp[1] = s1; pp[2] = s2;
+                int nxs[NNPE];
+                JF_UNROLL for (int k = 0; k < NNPE; k++) nxs[k] = xsl[n[k]];
+                SField X{Xs, nxs};
+                SField F[NF];
+                F[0].base = xs; F[0].n = n;
+                if (NF == 2) { F[NF - 1].base = us; F[NF - 1].n = n; }
+                if (NNPE == 10) ok = tet10_general(pt, el, F, X, out);
+                else if (NNPE == 8) ok = hex8_general(pt, el, F, X, out);
+                else ok = tet4_general(pt, el, F, X, out);
             }
-        } else {
-            double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
-            py[0] = s0; py[1] = s1; py[2] = s2;
+            if (!ok) atomicOr(a.fail, 1);
         }
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 3] = clock64();
+        if (G == 2) named_arrive(3 + (grp ^ 1), 2 * T);
+        if (G == 1) __syncthreads(); else named_sync(1 + grp, T);
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 4] = clock64();
+
+        // ---- (d) start the next patch's gather (its blob was requested at (b))
+        if (has_next) {
+            mbar_wait(&mbar[buf ^ 1], ((it + 1) >> 1) & 1);
+            if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 7] = clock64();
+            patch_gather_async<T, NF>(a, blob0 + (size_t)(buf ^ 1) * a.stride, tid, xs, Xs, us);
+        }
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 5] = clock64();
+
+        // ---- (e) phase 2: one thread per node: ordered reduction of the node's contiguous staged run (3 planes)
+        for (int j = tid; j < np; j += T) {
+            const int q0 = go[j], q1 = go[j + 1];
+            const double *sp = stage + q0;
+            const int cnt = q1 - q0;
+            double s0 = 0, s1 = 0, s2 = 0;
+            int q = 0;
+            for (; q + 2 <= cnt; q += 2) {
+                const double a0 = sp[q], a1 = sp[q + 1], b0 = sp[PS + q], b1 = sp[PS + q + 1], c0 = sp[2 * PS + q], c1 = sp[2 * PS + q + 1];
+                s0 += a0; s1 += b0; s2 += c0;
+                s0 += a1; s1 += b1; s2 += c1;
+            }
+            if (q < cnt) { s0 += sp[q]; s1 += sp[PS + q]; s2 += sp[2 * PS + q]; }
+            const uint32_t w = pn[j];
+            if (a.project) {
+                if (w & (1u << PN_FIXSHIFT)) s0 = 0.0;
+                if (w & (2u << PN_FIXSHIFT)) s1 = 0.0;
+                if (w & (4u << PN_FIXSHIFT)) s2 = 0.0;
+            }
+            if (j < nif) {
+                if (a.atomic_iface) {
+                    double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
+                    atomicAdd(py, s0); atomicAdd(py + 1, s1); atomicAdd(py + 2, s2);
+                } else {
+                    double *pp = a.ipart + 3 * ((long long)ipb + j);
+                    pp[0] = s0; pp[1] = s1; pp[2] = s2;
+                }
+            } else {
+                double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
+                py[0] = s0; py[1] = s1; py[2] = s2;
+            }
+        }
+        if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 6] = clock64();
+        // no barrier here: the in-flight gather writes only xs/Xs/us, which phase 2 does not read
     }
 }
 
-// y[interface node] = sum of its partial slots, ascending (set, patch) order.  3 threads per node.
-__global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const int32_t *__restrict__ iptr,
+// y[interface node] = sum of its partial slots, ascending (set, patch) order.  3 threads per node; the first four
+// slots come from one 16-byte load (islot4), rarer nodes with more slots continue through the CSR list.
+__global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const int4 *__restrict__ islot4, const int32_t *__restrict__ iptr,
                                     const int32_t *__restrict__ islots, const double *__restrict__ ipart,
                                     double *__restrict__ y, long long n3, const int *done) {
     if (done && *done) return;
@@ -129,8 +257,19 @@ __global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const i
     if (i >= n3) return;
     const int node = (int)(i / 3), c = (int)(i - 3LL * node);
     const uint32_t w = inodes[node];
+    const int4 s4 = islot4[node];
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (s4.x >= 0) v0 = __ldcg(ipart + 3LL * s4.x + c);
+    if (s4.y >= 0) v1 = __ldcg(ipart + 3LL * s4.y + c);
+    if (s4.z >= 0) v2 = __ldcg(ipart + 3LL * s4.z + c);
+    if (s4.w >= 0) v3 = __ldcg(ipart + 3LL * s4.w + c);
     double s = 0;
-    for (int q = iptr[node]; q < iptr[node + 1]; q++) s += ipart[3LL * islots[q] + c];
+    if (s4.x >= 0) s += v0;
+    if (s4.y >= 0) s += v1;
+    if (s4.z >= 0) s += v2;
+    if (s4.w >= 0) s += v3;
+    if (w & PN_NEEDX)   // overflow flag: more than four patches touch this node
+        for (int q = iptr[node] + 4; q < iptr[node + 1]; q++) s += __ldcg(ipart + 3LL * islots[q] + c);
     y[3LL * (w & PN_ID_MASK) + c] = s;
 }
 
@@ -156,13 +295,18 @@ static void apply_fixed_words(jfem_handle *h, std::vector<uint32_t> &words) {
 int upload_fixed(jfem_handle *h) {   // (re)upload everything that embeds the Dirichlet mask
     if (!h->built) return JFEM_OK;
     for (int c = 0; c < N_CLASSES; c++) {
-        if (h->hsets[c].n_elems == 0) continue;
-        std::vector<uint32_t> w = h->hsets[c].pnodes;
+        PatchSetHost &S = h->hsets[c];
+        if (S.n_elems == 0) continue;
+        std::vector<uint32_t> w = S.pnodes;
         apply_fixed_words(h, w);
-        JFEM_TRY(h->dsets[c].pnodes.upload(w));
+        for (int p = 0; p < S.n_patches; p++)
+            memcpy(&S.blob[(size_t)p * S.stride + S.off_pn], &w[S.pnode_ptr[p]], 4 * (size_t)(S.pnode_ptr[p + 1] - S.pnode_ptr[p]));
+        JFEM_TRY(h->dsets[c].blob.upload(S.blob));
     }
     std::vector<uint32_t> w = h->hif.inodes;
     apply_fixed_words(h, w);
+    for (size_t i = 0; i < w.size(); i++)
+        if (h->hif.iptr[i + 1] - h->hif.iptr[i] > 4) w[i] |= PN_NEEDX; else w[i] &= ~PN_NEEDX;   // bit 27 = overflow flag here
     JFEM_TRY(h->inodes.upload(w));
     JFEM_TRY(h->fixed.upload(h->mesh.fixed));
     return JFEM_OK;
@@ -185,17 +329,15 @@ int ensure_built(jfem_handle *h) {
         D.n_elems = S.n_elems; D.elem_offset = off;
         for (int64_t i = 0; i < S.n_elems; i++) e2i[S.elem_perm[i]] = off + i;
         off += S.n_elems;
-        if (S.n_elems == 0) continue;
-        JFEM_TRY(D.pnode_ptr.upload(S.pnode_ptr));
-        JFEM_TRY(D.n_iface.upload(S.n_iface));
-        JFEM_TRY(D.ipart_base.upload(S.ipart_base));
-        JFEM_TRY(D.lconn.upload(S.lconn));
-        JFEM_TRY(D.goff.upload(S.goff));
-        JFEM_TRY(D.gslots.upload(S.gslots));
-        // host copies of the big tables are no longer needed
-        std::vector<uint16_t>().swap(S.lconn);
-        std::vector<uint16_t>().swap(S.gslots);
-        std::vector<uint16_t>().swap(S.goff);
+        D.max_nx = S.max_nx; D.off_pn = S.off_pn; D.off_xl = S.off_xl; D.off_xs = S.off_xs; D.off_go = S.off_go; D.off_gs = S.off_gs; D.off_lc = S.off_lc;
+        D.stride = S.stride;
+    }
+    {
+        const size_t ni = h->hif.inodes.size();
+        std::vector<int32_t> s4(4 * ni, -1);
+        for (size_t i = 0; i < ni; i++)
+            for (int q = h->hif.iptr[i], k = 0; q < h->hif.iptr[i + 1] && k < 4; q++, k++) s4[4 * i + k] = h->hif.islots[q];
+        JFEM_TRY(h->islot4.upload(s4));
     }
     JFEM_TRY(h->e2i.upload(e2i));
     JFEM_TRY(h->iptr.upload(h->hif.iptr));
@@ -221,15 +363,26 @@ int ensure_built(jfem_handle *h) {
 template <int NNPE, int CLS, int MODE, class Pt, int T>
 static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const Pt &pt) {
     constexpr int NF = Pt::NF;
-    size_t smem = sizeof(double) * (3 * NNPE * T + (size_t)3 * D.max_nodes * (NF == 2 ? 3 : 2));
-    auto kern = patch_kernel<NNPE, CLS, MODE, Pt, T>;
+    constexpr int G = (PatchCfg<NNPE, CLS, MODE>::fast && T <= 256) ? 2 : 1;
+    size_t gsm = 16 + 2 * (size_t)D.stride + sizeof(double) * (3 * (NNPE * T + 5) + 1 + (size_t)3 * D.max_nodes * (NF == 2 ? 2 : 1) + (size_t)3 * D.max_nx);
+    gsm = (gsm + 127) & ~(size_t)127;
+    a.group_smem = (int)gsm;
+    size_t smem = gsm * G;
+    if (G == 2 && smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
+    auto kern = patch_kernel<NNPE, CLS, MODE, Pt, T, G>;
     static size_t configured = 0;
     if (smem > configured) {
         JFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     if (smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
-    kern<<<D.n_patches, T, smem, h->stream>>>(a, pt);
+    int per_sm = 1;
+    JFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T * G, smem));
+    if (per_sm < 1) per_sm = 1;
+    h->last_smem = (int64_t)smem; h->last_blocks_per_sm = per_sm;
+    int grid = h->n_sms * per_sm;
+    if (grid * G > D.n_patches) grid = (D.n_patches + G - 1) / G;
+    kern<<<grid, T * G, smem, h->stream>>>(a, pt);
     JFEM_CUDA(cudaGetLastError());
     h->matvec_launches++;
     return JFEM_OK;
@@ -299,12 +452,12 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         const PatchSetDev &D = h->dsets[c];
         if (D.n_elems == 0) continue;
         PatchKArgs a;
-        a.pnode_ptr = D.pnode_ptr.p; a.pnodes = D.pnodes.p; a.n_iface = D.n_iface.p; a.ipart_base = D.ipart_base.p;
-        a.lconn = D.lconn.p; a.goff = D.goff.p; a.gslots = D.gslots.p;
+        a.blob = D.blob.p; a.n_patches = D.n_patches; a.stride = D.stride; a.off_pn = D.off_pn; a.off_xl = D.off_xl; a.off_xs = D.off_xs; a.off_go = D.off_go;
+        a.off_gs = D.off_gs; a.off_lc = D.off_lc; a.max_nx = D.max_nx;
         a.coords = h->coords.p; a.x = x; a.ulin = h->ulin.p; a.y = y; a.ipart = h->ipart.p;
-        a.n_elems = D.n_elems; a.elem_offset = D.elem_offset; a.max_nodes = D.max_nodes;
+        a.elem_offset = D.elem_offset; a.max_nodes = D.max_nodes;
         a.project = (flags & JFEM_PROJECT) ? 1 : 0; a.atomic_iface = atomic_iface;
-        a.fail = h->dflags.p; a.done = done;
+        a.fail = h->dflags.p; a.done = done; a.timing = h->timing.p;
         int rc;
         switch (h->mesh.nnpe) {
             case 10: rc = dispatch_threads<10>(h, D, a, mode); break;
@@ -314,7 +467,7 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         JFEM_TRY(rc);
     }
     if (!atomic_iface && n3) {
-        iface_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h->stream>>>(h->inodes.p, h->iptr.p, h->islots.p, h->ipart.p, y, n3, done);
+        iface_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h->stream>>>(h->inodes.p, (const int4 *)h->islot4.p, h->iptr.p, h->islots.p, h->ipart.p, y, n3, done);
         JFEM_CUDA(cudaGetLastError());
         h->matvec_launches++;
     }

@@ -4,7 +4,8 @@
 // exactly EP elements) so that one thread block owns EP elements and the ~EP*nnpe/valence nodes they
 // touch.  For every patch we store (i) its unique node list (interface nodes -- those touched by more
 // than one patch -- first), (ii) the element->local-node table in node-major order (coalesced u16
-// reads), (iii) the transposed table node->staged element outputs, which lets the kernel reduce
+// reads), (iii) the element->staging-position table (node-major staging: all contributions to one node are
+// contiguous), which lets the kernel reduce
 // element contributions per node in a FIXED order with no atomics (the deterministic replacement for
 // the 30 CUDA.@atomic adds of demos/gpu_assembly_tet10.jl:225-229 and the owner-computes gather of
 // ext/JuliaFEMCUDAExt.jl:293-361).  Interface nodes get one partial-sum slot per touching patch; a
@@ -12,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <cstring>
 
 #include "common.h"
 
@@ -150,6 +152,8 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
         S.lconn.assign((size_t)S.n_patches * nnpe * EP, 0xFFFF);
         S.goff.assign((size_t)S.pnode_ptr[S.n_patches] + S.n_patches, 0);
         S.gslots.assign((size_t)S.n_patches * EP * nnpe, 0);
+        S.xslot.assign((size_t)S.pnode_ptr[S.n_patches], 0xFFFF);
+        std::vector<int> nxs(S.n_patches, 0);
 #pragma omp parallel for schedule(dynamic, 64)
         for (int p = 0; p < S.n_patches; p++) {
             int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
@@ -166,10 +170,12 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
                 }
             std::vector<int> order(np);
             std::iota(order.begin(), order.end(), 0);
+            // interface nodes first; ascending id inside each class so that the flat (node, component) gathers and
+            // stores of the kernel hit consecutive addresses wherever the mesh numbering is locally contiguous
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
                 bool ia = touch[ids[a]] > 1, ib = touch[ids[b]] > 1;
                 if (ia != ib) return ia;
-                return cnt[a] > cnt[b];
+                return false;
             });
             std::vector<int> newpos(np);
             int nif = 0;
@@ -182,6 +188,9 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
                 S.pnodes[nb + q] = w;
             }
             S.n_iface[p] = nif;
+            int nx = 0;
+            for (int q = 0; q < np; q++) if (S.pnodes[nb + q] & PN_NEEDX) S.xslot[nb + q] = (uint16_t)nx++;
+            nxs[p] = nx;
             // offsets
             uint16_t *go = &S.goff[(size_t)nb + p];
             go[0] = 0;
@@ -194,10 +203,11 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
                 for (int k = 0; k < nnpe; k++) {
                     int q = newpos[local_of(m.conn[S.elem_perm[i] * nnpe + k])];
                     S.lconn[((size_t)p * nnpe + k) * EP + t] = (uint16_t)q;
-                    gs[fill[q]++] = (uint16_t)(3 * k * EP + t);
+                    gs[(size_t)k * EP + t] = (uint16_t)(fill[q]++ - go[q]);   // rank of this element among the node's contributions
                 }
             }
         }
+        for (int p = 0; p < S.n_patches; p++) S.max_nx = std::max(S.max_nx, nxs[p]);
         for (int p = 0; p < S.n_patches; p++) {
             S.ipart_base[p] = (int32_t)ipart_total;
             int nb = S.pnode_ptr[p];
@@ -206,6 +216,46 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
             if (ipart_total > 0x7FFFFFF0LL) { jfem_set_error("too many interface partial slots"); return JFEM_EINVAL; }
         }
     }
+    // pack the per-patch blobs
+    bool rank_overflow = false;
+    for (int c = 0; c < N_CLASSES; c++) {
+        PatchSetHost &S = sets[c];
+        if (S.n_elems == 0) continue;
+        auto r16 = [](int v) { return (v + 15) & ~15; };
+        S.off_pn = 16;
+        S.off_xl = S.off_pn + r16(4 * S.max_nodes);
+        S.off_xs = S.off_xl + r16(4 * S.max_nx);
+        S.off_go = S.off_xs + r16(2 * S.max_nodes);
+        S.off_gs = S.off_go + r16(2 * (S.max_nodes + 1));
+        S.off_lc = S.off_gs + r16(EP * nnpe);
+        S.stride = S.off_lc + r16(2 * EP * nnpe);
+        S.blob.assign((size_t)S.stride * S.n_patches, 0);
+#pragma omp parallel for schedule(static)
+        for (int p = 0; p < S.n_patches; p++) {
+            uint8_t *b = &S.blob[(size_t)p * S.stride];
+            const int nb = S.pnode_ptr[p], np = S.pnode_ptr[p + 1] - nb;
+            int nx = 0;
+            uint32_t *xl = reinterpret_cast<uint32_t *>(b + S.off_xl);
+            for (int q = 0; q < np; q++) if (S.pnodes[nb + q] & PN_NEEDX) xl[nx++] = S.pnodes[nb + q] & PN_ID_MASK;
+            if ((S.n_iface[p] | nx) > 0xFFFF) nx = 0xFFFF;   // cannot happen: np <= 65534
+            int32_t hdr[4] = {np, S.n_iface[p] | (nx << 16), S.ipart_base[p], (int32_t)std::min<int64_t>(EP, S.n_elems - (int64_t)p * EP)};
+            memcpy(b, hdr, 16);
+            memcpy(b + S.off_pn, &S.pnodes[nb], 4 * (size_t)np);
+            memcpy(b + S.off_xs, &S.xslot[nb], 2 * (size_t)np);
+            memcpy(b + S.off_go, &S.goff[(size_t)nb + p], 2 * (size_t)(np + 1));
+            for (int q = 0; q < EP * nnpe; q++) {
+                uint16_t r = S.gslots[(size_t)p * EP * nnpe + q];
+                b[S.off_gs + q] = (uint8_t)(r > 255 ? 255 : r);
+                if (r > 255) rank_overflow = true;
+            }
+            memcpy(b + S.off_lc, &S.lconn[(size_t)p * nnpe * EP], 2 * (size_t)EP * nnpe);
+        }
+        std::vector<uint16_t>().swap(S.lconn);
+        std::vector<uint16_t>().swap(S.gslots);
+        std::vector<uint16_t>().swap(S.goff);
+        std::vector<uint16_t>().swap(S.xslot);
+    }
+    if (rank_overflow) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
     // interface node -> partial slots (ascending slot = ascending (set, patch))
     std::stable_sort(ipairs.begin(), ipairs.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) { return a.first < b.first; });
     iface = InterfaceHost();

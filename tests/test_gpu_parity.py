@@ -58,7 +58,6 @@ def test_matvec_tet10_curved(L, oracle, jf):
     m = curved_tet10(jf.mesh)
     u = jf.mesh.test_vector(m.n_dofs)
     h = make(L, m)
-    assert h.info().n_affine_elems == 0 or True
     assert relerr(h.matvec(u), oracle.matfree(10, m.coords, m.conn, u, par=LE)) < TOL
     assert h.info().n_affine_elems == 0
 
@@ -70,9 +69,8 @@ def test_matvec_tet10_mixed_affine_and_curved(L, oracle, jf):
     m.coords[sel] += 0.01 * rng.standard_normal((int(sel.sum()), 3)) / 12
     u = jf.mesh.test_vector(m.n_dofs)
     h = make(L, m)
-    na = h.info().n_affine_elems
     assert relerr(h.matvec(u), oracle.matfree(10, m.coords, m.conn, u, par=LE)) < TOL
-    assert 0 < na < m.n_elems
+    assert 0 < h.info().n_affine_elems < m.n_elems          # two launches: affine closed form + isoparametric
 
 
 def test_matvec_reference_fixture_mesh(L, oracle, jf):
@@ -317,10 +315,12 @@ def test_newton_krylov_neo_hookean(L, oracle, jf):
     h.set_dirichlet(fixed)
     top = np.nonzero(np.abs(m.coords[:, 2] - 1.0) < 1e-12)[0]
     fext = np.zeros(m.n_dofs)
-    fext[3 * top + 2] = -2e3 / top.size * 30
-    u, nit, cgit, res, hist = h.newton_krylov(fext, newton_tol=1e-6, max_newton=30, max_cg_per_newton=2000)
+    fext[3 * top + 2] = -6e3 / top.size          # ~0.1 tip deflection on a 3 x 1 x 1 beam with E = 3e6: clearly nonlinear
+    # the reference's forcing term eta = min(forcing_max, ||R||^0.5) is norm-unit dependent; with forces of O(1e3) its
+    # default forcing_max = 0.9 would only ask for a 10 % reduction per linear solve, so tighten it for this test
+    u, nit, cgit, res, hist = h.newton_krylov(fext, newton_tol=1e-6, max_newton=30, max_cg_per_newton=4000, forcing_max=1e-3)
     assert res < 1e-6 and 1 < nit <= 30 and len(hist) == nit and cgit == sum(c for c, _, _ in hist)
-    assert all(abs(eta - min(0.9, rn ** 0.5)) < 1e-12 for _, rn, eta in hist)      # ext/JuliaFEMCUDAExt.jl:819
+    assert all(abs(eta - min(1e-3, rn ** 0.5)) < 1e-12 for _, rn, eta in hist)     # ext/JuliaFEMCUDAExt.jl:819
     R = fext - oracle.matfree(10, m.coords, m.conn, u, kind=1, par=NH, finite_strain=True)
     R[fixed - 1] = 0
     assert np.linalg.norm(R) < 1e-5
