@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--patch", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -170,36 +171,23 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from juliafem.jl_b200.distributed import PartitionedProblem, torch_all_gather_object, torch_broadcast_bytes
     m = build_mesh(args.workload, world)
     et = m.elem_type
     fixed_g = mesh.clamp_dofs(m)
     total_dofs = m.n_dofs
-    if world > 1:
-        part = mesh.partition_mesh(m, world, rank)
-        coords_l, conn_l = m.coords[part.local_nodes - 1], part.conn_local
-        h = _lib.Handle(et, coords_l, conn_l, device=local_rank)
-        g2l = np.zeros(m.n_nodes + 1, dtype=np.int64)
-        g2l[part.local_nodes] = np.arange(1, part.local_nodes.size + 1)
-        fn = (fixed_g - 1) // 3 + 1
-        keep = g2l[fn] > 0
-        fixed = 3 * (g2l[fn[keep]] - 1) + ((fixed_g[keep] - 1) % 3) + 1
-        n_local_dofs, n_own_dofs = 3 * part.local_nodes.size, 3 * part.n_owned
-    else:
-        h = _lib.Handle(et, m.coords, m.conn, device=local_rank)
-        fixed, n_local_dofs, n_own_dofs = fixed_g, m.n_dofs, m.n_dofs
-    if args.patch:
-        h.set_option("patch_elems", args.patch)
-    h.set_material(_lib.MAT_LINEAR_ELASTIC, (210e9, 0.3))
-    h.set_dirichlet(fixed)
+    pp = PartitionedProblem(m, rank, world, local_rank, material=(_lib.MAT_LINEAR_ELASTIC, (210e9, 0.3)), fixed_dofs=fixed_g,
+                            options={"patch_elems": args.patch} if args.patch else None)
+    h = pp.handle
+    n_local_dofs, n_own_dofs = 3 * pp.local_nodes.size, 3 * pp.n_owned
     h.set_stream(torch.cuda.current_stream().cuda_stream)
     if world > 1:
-        uid = [_lib.Handle.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0, device=dev)
-        h.comm_init(world, rank, uid[0], part.n_owned)
-        h.comm_set_halo(part.send, part.recv)
+        pp.init_comm(torch_broadcast_bytes(dist, dev))
+        if not args.nccl_halo:
+            pp.init_p2p(torch_all_gather_object(dist))
 
     u_full = mesh.test_vector(total_dofs, fixed_g)
-    u_host = u_full if world == 1 else u_full.reshape(-1, 3)[part.local_nodes - 1].ravel().copy()
+    u_host = pp.scatter_vector(u_full)
     x = torch.from_numpy(u_host).to(dev)
     y = torch.empty_like(x)
     flush = None if args.no_flush else torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -271,7 +259,8 @@ def main():
                                    f"linear elastic E=210e9 nu=0.3, clamp x=0, deterministic scatter",
                        "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
                        "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems), "smem_bytes": int(info.smem_bytes), "blocks_per_sm": int(info.blocks_per_sm), "interface_nodes": int(info.n_interface_nodes),
-                       "partition": "z-slabs by contiguous node range, owner-computes + ghost elements" if world > 1 else "single GPU",
+                       "partition": ("z-slabs by contiguous node range, owner-computes + ghost elements; halo via "
+                                     + ("ncclSend/ncclRecv" if args.nccl_halo else "peer-memory stores over NVLink (CUDA IPC)")) if world > 1 else "single GPU",
                        "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds)},
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
                     "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},

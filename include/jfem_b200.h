@@ -141,6 +141,13 @@ int jfem_comm_init(jfem_handle *h, int n_ranks, int rank, const char *id128, int
 int jfem_comm_set_halo(jfem_handle *h, int n_neighbours, const int32_t *neighbour_rank,
                        const int64_t *send_ptr, const int32_t *send_nodes,
                        const int64_t *recv_ptr, const int32_t *recv_nodes);
+/* optional: replace the NCCL send/recv halo by direct peer-memory stores over NVLink (CUDA IPC, same node).
+ * export: returns 128 bytes (two cudaIpcMemHandle_t: landing buffer, flags); the host all-gathers them.
+ * import: all_handles = n_ranks x 128 bytes; recv_offsets[r*n_ranks+s] = node offset of rank s's segment inside rank r's
+ * landing buffer (= recv_ptr of r for neighbour s, -1 if none); halves[r] = landing-buffer half size of rank r in doubles
+ * (3*total_recv_nodes+8). */
+int jfem_comm_p2p_export(jfem_handle *h, char *handles128);
+int jfem_comm_p2p_import(jfem_handle *h, const char *all_handles, const int64_t *recv_offsets, const int64_t *halves);
 int jfem_comm_destroy(jfem_handle *h);
 
 #ifdef __cplusplus

@@ -24,7 +24,8 @@ EXPORTS = [
     "jfem_set_material", "jfem_set_dirichlet", "jfem_get_info", "jfem_set_stream", "jfem_synchronize", "jfem_matvec",
     "jfem_internal_force", "jfem_set_linearization", "jfem_commit_state", "jfem_get_state", "jfem_set_state",
     "jfem_element_matrices", "jfem_csr_size", "jfem_csr_pattern", "jfem_assemble_csr", "jfem_spmv", "jfem_cg",
-    "jfem_newton_krylov", "jfem_comm_unique_id", "jfem_comm_init", "jfem_comm_set_halo", "jfem_comm_destroy",
+    "jfem_newton_krylov", "jfem_comm_unique_id", "jfem_comm_init", "jfem_comm_set_halo", "jfem_comm_p2p_export",
+    "jfem_comm_p2p_import", "jfem_comm_destroy",
 ]
 
 
@@ -87,6 +88,8 @@ def lib():
         L.jfem_comm_unique_id.argtypes = [C.c_char_p]
         L.jfem_comm_init.argtypes = [vp, i32, i32, C.c_char_p, i64]
         L.jfem_comm_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+        L.jfem_comm_p2p_export.argtypes = [vp, C.c_char_p]
+        L.jfem_comm_p2p_import.argtypes = [vp, C.c_char_p, vp, vp]
         L.jfem_comm_destroy.argtypes = [vp]
         for name in EXPORTS:
             if name != "jfem_last_error":
@@ -301,3 +304,14 @@ class Handle:
         rna = np.ascontiguousarray(np.concatenate(rn) if rn else np.zeros(0), dtype=np.int32)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
         check(lib().jfem_comm_set_halo(self._h, len(nbs), vp(nb), vp(spa), vp(sna), vp(rpa), vp(rna)))
+        self._halo_nbs, self._halo_recv_ptr = nbs, rp
+
+    def comm_p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().jfem_comm_p2p_export(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_import(self, all_handles: bytes, recv_offsets, halves):
+        ro = np.ascontiguousarray(recv_offsets, dtype=np.int64)
+        hv = np.ascontiguousarray(halves, dtype=np.int64)
+        check(lib().jfem_comm_p2p_import(self._h, all_handles, ro.ctypes.data_as(C.c_void_p), hv.ctypes.data_as(C.c_void_p)))

@@ -68,6 +68,17 @@ struct jfem_handle {
     std::vector<int64_t> send_ptr, recv_ptr;
     DevBuf<int32_t> send_nodes, recv_nodes;
     DevBuf<double> send_buf, recv_buf;
+    // peer-to-peer halo (CUDA IPC)
+    bool p2p_ready = false;
+    unsigned long long p2p_seq = 0;
+    size_t p2p_half = 0;
+    DevBuf<double> p2p_land;
+    DevBuf<unsigned long long> p2p_flags;
+    DevBuf<unsigned int> p2p_ticket;
+    std::vector<double *> p2p_peer_land;
+    std::vector<unsigned long long *> p2p_peer_flag;
+    std::vector<int64_t> p2p_peer_off;
+    std::vector<size_t> p2p_peer_half;
     // stats
     int64_t matvec_launches = 0, total_launches = 0, last_smem = 0, last_blocks_per_sm = 0;
 
