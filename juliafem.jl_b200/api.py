@@ -1,0 +1,500 @@
+"""Python host mirror of the reference's user-facing interface for the elasticity hot path.
+
+Julia is not available in the build image, so the host side above the C ABI is written here with the reference's
+names and argument meaning (`!` becomes a trailing underscore); the Julia shim with the same calls is
+juliafem.jl_b200/julia/JuliaFEMB200.jl.  Two seams are served:
+
+  seam 1 (new API)      Physics / Element / add_elements_ / add_dirichlet_ / add_neumann_ / solve_(physics, backend=GPU())
+                        -> initialize_backend / solve_backend_ -> ElasticitySolution
+                        (src/physics.jl:128-156,222 ; src/backend/abstract.jl:138-145,181-217,228,241 ;
+                         ext/JuliaFEMCUDAExt.jl:86-217,867-916 ; demos/cantilever_physics_gpu.jl:50-136)
+  seam 2 (classic API)  Problem(Elasticity|Dirichlet) / update_ / add_elements_ / Analysis(Linear|Nonlinear) / assemble_ / run_
+                        (src/assembly/problems.jl:14-40,95-105 ; src/assembly/assembly.jl:31 ; src/analysis.jl:7-13 ;
+                         src/solvers.jl:192-216,575-641 ; src/problems_dirichlet.jl:60-90 ; examples/linear_static.jl:23-100)
+
+All heavy arithmetic (element integration, scatter, K.u, CG, Newton-Krylov) runs in libjfem_b200.so on the GPU; there is
+no CPU fallback.  What stays on the host is bookkeeping: node renumbering, load vectors, boundary-condition lists.
+"""
+from __future__ import annotations
+
+import time as _time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+# element topologies (src/topology/tetrahedra.jl:73-105, hexahedra.jl:14-18, surfaces for loads)
+Tet4, Hex8, Tet10, Tri3, Tri6, Quad4, Poi1 = "Tet4", "Hex8", "Tet10", "Tri3", "Tri6", "Quad4", "Poi1"
+_NNPE = {Tet4: 4, Hex8: 8, Tet10: 10, Tri3: 3, Tri6: 6, Quad4: 4, Poi1: 1}
+_VOLUME = (Tet4, Hex8, Tet10)
+
+
+class Elasticity:
+    """Problem properties of src/problems_elasticity.jl:36-46."""
+
+    def __init__(self):
+        self.formulation = "continuum"
+        self.finite_strain = False
+        self.geometric_stiffness = False
+        self.store_fields = []
+
+
+class Dirichlet:
+    pass
+
+
+class Linear:
+    pass
+
+
+class Nonlinear:
+    """Solver knobs of src/solvers.jl:539-551 (max_iterations, convergence_tolerance on ||du||)."""
+    max_iterations = 10
+    convergence_tolerance = 5.0e-5
+
+
+@dataclass
+class LinearElastic:          # src/materials/linear_elastic.jl:51-56
+    E: float
+    nu: float
+
+
+@dataclass
+class NeoHookean:             # src/materials/neo_hookean.jl:87-100 (E_mod, nu keywords)
+    E_mod: float = 3e6
+    nu: float = 0.45
+
+
+@dataclass
+class PerfectPlasticity:      # src/materials/perfect_plasticity.jl:166-181
+    E: float
+    nu: float
+    sigma_y: float
+    H: float = 0.0
+
+
+class GPU:                    # src/backend/abstract.jl:61-65
+    def __init__(self, device: int = 0):
+        self.device = device
+
+
+class CPU:
+    def __init__(self, nthreads: int = 1):
+        self.nthreads = nthreads
+
+
+class Element:
+    """Immutable element (src/elements/elements.jl:70-76): topology, connectivity (node ids, 1-based), named fields."""
+
+    def __init__(self, topology, connectivity, fields=None, id=-1):
+        if topology not in _NNPE:
+            raise ValueError(f"unknown element topology {topology}")
+        if len(connectivity) != _NNPE[topology]:
+            raise ValueError(f"{topology} needs {_NNPE[topology]} nodes")
+        self.topology, self.connectivity, self.id = topology, tuple(int(c) for c in connectivity), id
+        self.fields = dict(fields or {})
+
+    def __call__(self, name):
+        return self.fields[name]
+
+
+def update_(elements, name, value):
+    """update!(elements, "youngs modulus", 208.0e3)  (time-independent fields only)"""
+    for el in (elements if isinstance(elements, (list, tuple)) else [elements]):
+        el.fields[name] = value
+
+
+def _nodes_by_rows(X, nn):
+    """The reference stores element geometry as a 3 x nnpe matrix (one column per node, ext/JuliaFEMCUDAExt.jl:117);
+    an (nnpe, 3) array is accepted too when unambiguous."""
+    X = np.asarray(X, dtype=np.float64)
+    if X.shape == (3, nn):
+        return X.T
+    if X.shape == (nn, 3):
+        return X
+    raise ValueError(f"geometry must be 3 x {nn}")
+
+
+def _get(el, *names, default=None):
+    for n in names:
+        if n in el.fields:
+            return el.fields[n]
+    return default
+
+
+# ------------------------------------------------------------------------------------------------ seam 1
+
+@dataclass
+class DirichletBC:            # src/physics.jl:42-52
+    node_ids: list = field(default_factory=list)
+    components: list = field(default_factory=list)
+    values: list = field(default_factory=list)
+
+
+@dataclass
+class NeumannBC:              # src/physics.jl:54-64
+    surface_elements: list = field(default_factory=list)
+    traction: list = field(default_factory=list)
+
+
+@dataclass
+class ElasticitySolution:     # src/backend/abstract.jl:138-145
+    u: np.ndarray
+    newton_iterations: int
+    cg_iterations: int
+    residual: float
+    solve_time: float
+    history: list
+
+
+class Physics:
+    """Physics(Elasticity, "name", 3)  (src/physics.jl:128-156)"""
+
+    def __init__(self, kind=Elasticity, name="physics", dimension=3):
+        if dimension != 3:
+            raise ValueError("only 3D continuum elasticity is on the accelerated path")
+        self.name, self.dimension = name, dimension
+        self.properties = kind() if isinstance(kind, type) else kind
+        self.body_elements: list = []
+        self.bc_dirichlet = DirichletBC()
+        self.bc_neumann = NeumannBC()
+        self.material = None
+
+
+def add_elements_(target, elements):
+    if isinstance(target, Physics):
+        target.body_elements.extend(elements)
+    else:
+        target.elements.extend(elements)
+
+
+def add_dirichlet_(physics: Physics, node_ids, components, value=0.0):
+    """add_dirichlet!(physics, [node], [1,2,3], 0.0)  (src/physics.jl:222)"""
+    physics.bc_dirichlet.node_ids.append(list(node_ids))
+    physics.bc_dirichlet.components.append(list(components))
+    physics.bc_dirichlet.values.append(float(value))
+
+
+def add_neumann_(physics: Physics, surface_element: Element, traction):
+    physics.bc_neumann.surface_elements.append(surface_element)
+    physics.bc_neumann.traction.append(np.asarray(traction, dtype=np.float64))
+
+
+def _material_of(elements, properties, explicit=None):
+    """(kind, params) for jfem_set_material from the element fields / an explicit material struct."""
+    if isinstance(explicit, NeoHookean):
+        return _lib.MAT_NEO_HOOKEAN, (explicit.E_mod, explicit.nu)
+    if isinstance(explicit, PerfectPlasticity):
+        return _lib.MAT_PERFECT_PLASTICITY, (explicit.E, explicit.nu, explicit.sigma_y, explicit.H)
+    if isinstance(explicit, LinearElastic):
+        return _lib.MAT_LINEAR_ELASTIC, (explicit.E, explicit.nu)
+    E = {_get(el, "youngs modulus", "youngs_modulus") for el in elements}
+    nu = {_get(el, "poissons ratio", "poissons_ratio") for el in elements}
+    if None in E or None in nu:
+        raise KeyError("elements need \"youngs modulus\" and \"poissons ratio\" fields")   # reference: KeyError from element(...)
+    if len(E) != 1 or len(nu) != 1:
+        raise NotImplementedError("per-element material parameters are not supported yet (homogeneous only)")
+    if getattr(properties, "finite_strain", False):
+        return _lib.MAT_NEO_HOOKEAN, (E.pop(), nu.pop())
+    return _lib.MAT_LINEAR_ELASTIC, (E.pop(), nu.pop())
+
+
+class ElasticityDataGPU:
+    """Device-side data of one problem (ext/JuliaFEMCUDAExt.jl:34-60): owns the jfem handle."""
+
+    def __init__(self, elements, dirichlet: DirichletBC, neumann: NeumannBC, properties, material=None, device=0, options=None):
+        vol = [el for el in elements if el.topology in _VOLUME]
+        if not vol:
+            raise ValueError("no volume elements")
+        bad = [el for el in elements if el.topology not in _VOLUME]
+        if bad:
+            # same refusal as assemble! for e.g. Seg3 in a 3D problem (src/problems_elasticity.jl:510-518)
+            raise ValueError(f"unsupported element type {bad[0].topology} in a 3D continuum problem")
+        kinds = {el.topology for el in vol}
+        if len(kinds) != 1:
+            raise NotImplementedError("one element type per problem on the accelerated path")
+        self.topology = kinds.pop()
+        nnpe = _NNPE[self.topology]
+        # node renumbering: sorted unique ids -> 1..n (ext:100-108)
+        conn = np.array([el.connectivity for el in vol], dtype=np.int64)
+        self.node_ids = np.unique(conn)
+        remap = {int(n): i + 1 for i, n in enumerate(self.node_ids)}
+        self.conn = np.vectorize(remap.__getitem__)(conn).astype(np.int32)
+        coords = np.zeros((self.node_ids.size, 3))
+        for el, c in zip(vol, self.conn):
+            X = np.asarray(_get(el, "geometry"), dtype=np.float64)
+            X = _nodes_by_rows(X, nnpe)
+            coords[c - 1] = X
+        self.coords = coords
+        self.n_nodes, self.n_dofs = coords.shape[0], 3 * coords.shape[0]
+        self.handle = _lib.Handle(nnpe, coords, self.conn, device=device)
+        for k, v in (options or {}).items():
+            self.handle.set_option(k, v)
+        self.handle.set_material(*_material_of(vol, properties, material))
+        # Dirichlet: is_fixed / prescribed per dof (ext:144-158)
+        dofs, vals = [], []
+        for nodes, comps, val in zip(dirichlet.node_ids, dirichlet.components, dirichlet.values):
+            for n in nodes:
+                for c in comps:
+                    dofs.append(3 * (remap[int(n)] - 1) + int(c))
+                    vals.append(val)
+        self.fixed_dofs = np.array(dofs, dtype=np.int64)
+        self.prescribed = np.zeros(self.n_dofs)
+        if dofs:
+            self.prescribed[self.fixed_dofs - 1] = vals
+        self.handle.set_dirichlet(self.fixed_dofs, np.array(vals))
+        # external load: Tri3 lumped traction area/3 * t exactly as apply_surface_traction_kernel! (ext:368-416)
+        self.f_ext = np.zeros(self.n_dofs)
+        for surf, t in zip(neumann.surface_elements, neumann.traction):
+            self.f_ext += surface_traction(surf, t, remap, self.n_dofs)
+
+    def close(self):
+        self.handle.close()
+
+
+def surface_traction(surf: Element, traction, remap, n_dofs):
+    """Nodal forces of a constant traction on one surface element.  Tri3: lumped area/3 (the reference's GPU kernel,
+    ext/JuliaFEMCUDAExt.jl:368-416); Tri6 / Quad4: consistent (src/problems_elasticity.jl:454-502)."""
+    f = np.zeros(n_dofs)
+    X = np.asarray(_get(surf, "geometry"), dtype=np.float64)
+    nn = _NNPE[surf.topology]
+    X = _nodes_by_rows(X, nn)
+    ids = [remap[int(n)] for n in surf.connectivity]
+    t = np.asarray(traction, dtype=np.float64)
+    if surf.topology == Tri3:
+        area = 0.5 * np.linalg.norm(np.cross(X[1] - X[0], X[2] - X[0]))
+        w = np.full(3, area / 3.0)
+    elif surf.topology == Tri6:
+        # GLTRI3 (degree 2) on the quadratic triangle: consistent load
+        pts = [(1 / 6, 1 / 6), (2 / 3, 1 / 6), (1 / 6, 2 / 3)]
+        w = np.zeros(6)
+        for u, v in pts:
+            L = 1 - u - v
+            N = np.array([L * (2 * L - 1), u * (2 * u - 1), v * (2 * v - 1), 4 * L * u, 4 * u * v, 4 * v * L])
+            dNu = np.array([-(4 * L - 1), 4 * u - 1, 0, 4 * (L - u), 4 * v, -4 * v])
+            dNv = np.array([-(4 * L - 1), 0, 4 * v - 1, -4 * u, 4 * u, 4 * (L - v)])
+            w += N * np.linalg.norm(np.cross(dNu @ X, dNv @ X)) / 6.0
+    elif surf.topology == Quad4:
+        a = 0.5773502691896258
+        w = np.zeros(4)
+        s = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], float)
+        for u in (-a, a):
+            for v in (-a, a):
+                N = 0.25 * (1 + s[:, 0] * u) * (1 + s[:, 1] * v)
+                dNu = 0.25 * s[:, 0] * (1 + s[:, 1] * v)
+                dNv = 0.25 * s[:, 1] * (1 + s[:, 0] * u)
+                w += N * np.linalg.norm(np.cross(dNu @ X, dNv @ X))
+    else:
+        raise ValueError(f"unsupported surface element {surf.topology}")
+    for i, n in enumerate(ids):
+        f[3 * (n - 1):3 * n] += w[i] * t
+    return f
+
+
+def initialize_backend(backend, physics: Physics, time=0.0, options=None):
+    """initialize_backend(::GPU, physics, time)  (ext/JuliaFEMCUDAExt.jl:867-869)"""
+    if not isinstance(backend, GPU):
+        raise NotImplementedError("this package provides the GPU backend only (no CPU fallback)")
+    return ElasticityDataGPU(physics.body_elements, physics.bc_dirichlet, physics.bc_neumann, physics.properties,
+                             material=physics.material, device=backend.device, options=options)
+
+
+def solve_backend_(data: ElasticityDataGPU, physics: Physics = None, tol=1e-6, max_iter=1000, newton_tol=1e-6, max_newton=20,
+                   max_cg_per_newton=50, forcing_power=0.5, forcing_max=0.9):
+    """solve_backend!(data, physics; ...) -> (u, newton_iters, cg_iters, residual, history)   (ext:886-916).
+    Linear elastic: one projected CG solve of K u = f - K u_B with the reference's absolute stop sqrt(r.r) < tol
+    (ext:531-577).  Nonlinear materials: inexact Newton-Krylov with the Eisenstat-Walker forcing of ext:819-820."""
+    h = data.handle
+    nonlinear = physics is not None and (getattr(physics.properties, "finite_strain", False)
+                                          or isinstance(physics.material, (NeoHookean, PerfectPlasticity)))
+    if nonlinear:
+        u0 = data.prescribed.copy()
+        u, nit, cgit, res, hist = h.newton_krylov(data.f_ext, u0, newton_tol=newton_tol, max_newton=max_newton,
+                                                  max_cg_per_newton=max_cg_per_newton, forcing_power=forcing_power, forcing_max=forcing_max)
+        return u, nit, cgit, res, hist
+    b = data.f_ext
+    if np.any(data.prescribed):
+        b = b - h.matvec(data.prescribed)          # lifting: f_I - K_IB u_B   (src/solvers.jl:205-210)
+    x, it, res = h.cg(b, tol=tol, relative=False, max_iter=max_iter)
+    u = x + data.prescribed
+    rn = float(np.sqrt(np.sum(np.delete(b, data.fixed_dofs - 1) ** 2))) if data.fixed_dofs.size else float(np.linalg.norm(b))
+    return u, 1, it, res, [(it, rn, min(forcing_max, rn ** forcing_power) if rn > 0 else 0.0)]
+
+
+def solve_(physics: Physics, backend=None, time=0.0, tol=1e-6, max_iter=1000, newton_tol=1e-6, max_newton=20, max_cg_per_newton=50):
+    """solve!(physics; backend=GPU(), time, tol, max_iter, newton_tol, max_newton, max_cg_per_newton) -> ElasticitySolution
+    (src/backend/abstract.jl:181-217)"""
+    backend = GPU() if backend is None else backend
+    t0 = _time.perf_counter()
+    data = initialize_backend(backend, physics, time)
+    try:
+        u, nit, cgit, res, hist = solve_backend_(data, physics, tol=tol, max_iter=max_iter, newton_tol=newton_tol,
+                                                 max_newton=max_newton, max_cg_per_newton=max_cg_per_newton)
+    finally:
+        data.close()
+    return ElasticitySolution(u, nit, cgit, res, _time.perf_counter() - t0, hist)
+
+
+# ------------------------------------------------------------------------------------------------ seam 2
+
+class SparseMatrixCSR:
+    """What assemble_ leaves in problem.assembly.K: the reference stores COO triplets and converts with sparse()
+    (src/sparse/sparse.jl:53-55); here the already-summed CSR (== CSC of the symmetric pattern) comes back from the device."""
+
+    def __init__(self, rowptr, colind, vals, n):
+        self.rowptr, self.colind, self.vals, self.n = rowptr, colind, vals, n
+
+    def to_coo(self):
+        rows = np.repeat(np.arange(1, self.n + 1), np.diff(self.rowptr))
+        return rows, self.colind.copy(), self.vals.copy()       # I, J, V (1-based like SparseMatrixCOO)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals, self.colind - 1, self.rowptr - 1), shape=(self.n, self.n))
+
+
+class Assembly:               # src/assembly/problems.jl:14-40 (fields used on this path)
+    def __init__(self):
+        self.K = None
+        self.f = None
+        self.u = None
+
+
+class Problem:
+    """Problem(Elasticity, "name", 3) / Problem(Dirichlet, "fixed", 3, "displacement")  (src/assembly/problems.jl:95-105)"""
+
+    def __init__(self, kind, name, dimension, parent_field_name=None):
+        self.name, self.dimension, self.parent_field_name = name, dimension, parent_field_name
+        self.properties = kind() if isinstance(kind, type) else kind
+        self.elements: list = []
+        self.assembly = Assembly()
+        self.material = None
+        self._data = None
+
+
+def _dirichlet_from(problems):
+    bc = DirichletBC()
+    for p in problems:
+        if not isinstance(p.properties, Dirichlet):
+            continue
+        for el in p.elements:                       # nodal collocation (src/problems_dirichlet.jl:60-90)
+            for c in (1, 2, 3):
+                key = f"{p.parent_field_name or 'displacement'} {c}"
+                if key in el.fields:
+                    bc.node_ids.append(list(el.connectivity))
+                    bc.components.append([c])
+                    bc.values.append(float(el.fields[key]))
+    return bc
+
+
+def _body_load(data: ElasticityDataGPU, elements):
+    """f_ext += w N b for "displacement load i" fields (src/problems_elasticity.jl:412-426), host-side numpy."""
+    f = np.zeros(data.n_dofs)
+    loads = [(i, {_get(el, f"displacement load {i + 1}") for el in elements}) for i in range(3)]
+    loads = [(i, v.pop()) for i, v in loads if len(v) == 1 and None not in v]
+    if not loads:
+        return f
+    nn = data.conn.shape[1]
+    if nn == 10:
+        a, b = (5 + 3 * np.sqrt(5.0)) / 20, (5 - np.sqrt(5.0)) / 20
+        pts, wts = np.array([[a, b, b], [b, a, b], [b, b, a], [b, b, b]]), np.full(4, 1 / 24)
+    elif nn == 4:
+        pts, wts = np.array([[0.25, 0.25, 0.25]]), np.array([1 / 6])
+    else:
+        g = 0.5773502691896258
+        pts = np.array([[i, j, k] for k in (-g, g) for j in (-g, g) for i in (-g, g)])
+        wts = np.ones(8)
+    X = data.coords[data.conn - 1]                                   # (ne, nn, 3)
+    for xi, w in zip(pts, wts):
+        N, dN = _shape(nn, xi)
+        J = np.einsum("ia,eib->eab", dN, X)
+        wd = w * np.linalg.det(J)
+        for comp, bval in loads:
+            np.add.at(f, 3 * (data.conn - 1) + comp, wd[:, None] * N[None, :] * bval)
+    return f
+
+
+def _shape(nn, xi):
+    u, v, w = xi
+    if nn == 4:
+        N = np.array([1 - u - v - w, u, v, w])
+        dN = np.array([[-1, -1, -1], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    elif nn == 10:
+        L = 1 - u - v - w
+        N = np.array([L * (2 * L - 1), u * (2 * u - 1), v * (2 * v - 1), w * (2 * w - 1), 4 * L * u, 4 * u * v, 4 * L * v, 4 * L * w, 4 * u * w, 4 * v * w])
+        d = 1 - 4 * L
+        dN = np.array([[d, d, d], [4 * u - 1, 0, 0], [0, 4 * v - 1, 0], [0, 0, 4 * w - 1], [4 * (L - u), -4 * u, -4 * u], [4 * v, 4 * u, 0],
+                       [-4 * v, 4 * (L - v), -4 * v], [-4 * w, -4 * w, 4 * (L - w)], [4 * w, 0, 4 * u], [0, 4 * w, 4 * v]])
+    else:
+        s = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
+        N = 0.125 * (1 + s[:, 0] * u) * (1 + s[:, 1] * v) * (1 + s[:, 2] * w)
+        dN = 0.125 * np.stack([s[:, 0] * (1 + s[:, 1] * v) * (1 + s[:, 2] * w), s[:, 1] * (1 + s[:, 0] * u) * (1 + s[:, 2] * w),
+                               s[:, 2] * (1 + s[:, 0] * u) * (1 + s[:, 1] * v)], axis=1)
+    return N, dN
+
+
+def _ensure_data(problem: Problem, boundary=(), device=0):
+    if problem._data is None:
+        problem._data = ElasticityDataGPU(problem.elements, _dirichlet_from(boundary), NeumannBC(), problem.properties,
+                                          material=problem.material, device=device)
+        problem._data.f_ext += _body_load(problem._data, problem.elements)
+    return problem._data
+
+
+def assemble_(problem: Problem, time=0.0, u=None, symmetrise=False, device=0):
+    """assemble!(problem, time)  (src/assembly/assembly.jl:31): leaves K (assembled on the GPU: element integration +
+    coloured scatter into the reference's sparsity pattern) and f = f_ext - f_int in problem.assembly."""
+    if isinstance(problem.properties, Dirichlet):
+        return problem                      # boundary problems only contribute their dof lists (handled by the solver)
+    d = _ensure_data(problem, device=device)
+    rowptr, colind = d.handle.csr_pattern()
+    vals, fint = d.handle.assemble_csr(u, symmetrise=symmetrise, want_f=u is not None)
+    problem.assembly.K = SparseMatrixCSR(rowptr, colind, vals, d.n_dofs)
+    problem.assembly.f = d.f_ext - (fint if fint is not None else 0.0)
+    return problem
+
+
+class Analysis:
+    """Analysis(Linear, model, fixed)  (src/analysis.jl:7-13)"""
+
+    def __init__(self, kind, *problems, name="analysis"):
+        self.properties = kind() if isinstance(kind, type) else kind
+        self.problems = list(problems)
+        self.name = name
+        self.u = None
+        self.iterations = 0
+        self.cg_iterations = 0
+
+
+def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0):
+    """run!(analysis)  (src/solvers.jl:641 Linear, :575 Nonlinear).  The direct LDLt of solve!(...,Val{1})
+    (src/solvers.jl:192-216) is replaced by projected CG on the device with the same elimination semantics:
+    u_B = g, K_II u_I = f_I - K_IB u_B.  Default stop: ||r|| <= 1e-8 ||b|| (north_star)."""
+    field_problems = [p for p in analysis.problems if isinstance(p.properties, Elasticity)]
+    boundary = [p for p in analysis.problems if isinstance(p.properties, Dirichlet)]
+    if len(field_problems) != 1:
+        raise NotImplementedError("exactly one elasticity problem per analysis on the accelerated path")
+    model = field_problems[0]
+    model._data = None
+    d = _ensure_data(model, boundary, device=device)
+    h = d.handle
+    if isinstance(analysis.properties, Nonlinear) or model.properties.finite_strain or isinstance(model.material, (NeoHookean, PerfectPlasticity)):
+        u, nit, cgit, res, hist = h.newton_krylov(d.f_ext, d.prescribed.copy(), newton_tol=max(tol, 1e-12) if not relative else 1e-6,
+                                                  max_newton=max(20, getattr(analysis.properties, "max_iterations", 10)),
+                                                  max_cg_per_newton=max_iter, forcing_max=1e-3)
+        analysis.iterations, analysis.cg_iterations = nit, cgit
+    else:
+        b = d.f_ext - (h.matvec(d.prescribed) if np.any(d.prescribed) else 0.0)
+        x, it, res = h.cg(b, tol=tol, relative=relative, max_iter=max_iter)
+        u = x + d.prescribed
+        analysis.iterations, analysis.cg_iterations = 1, it
+    analysis.u = u
+    model.assembly.u = u
+    return analysis
+
+
+def nodal_displacements(problem_or_data, u):
+    """{node id: (ux, uy, uz)} in the caller's original node ids."""
+    d = problem_or_data._data if isinstance(problem_or_data, Problem) else problem_or_data
+    return {int(n): u[3 * i:3 * i + 3] for i, n in enumerate(d.node_ids)}
