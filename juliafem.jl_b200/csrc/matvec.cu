@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // Gathers and stores use the flat index i = 3*node + component so that a warp touches consecutive addresses wherever
 // consecutive patch nodes have consecutive ids (the patch node lists are id-sorted).
 
-// Ping-pong: a block holds G = 2 independent groups of T threads (when registers allow), each working on its own
+// Ping-pong: a block holds G = 2 (T = 256) or 3 (T = 128) independent groups of T threads (when registers allow), each working on its own
 // patch stream with its own shared-memory tiles.  Named barriers force the two groups to take turns in the fp64-bound
 // phase 1, so that one group's gather / reduction / store phases always overlap the other group's arithmetic
 // (two free-running blocks per SM were observed to run in lock-step instead: both in phase 1, then both in phase 2).
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
         mbar_fence_init();
     }
     __syncthreads();
-    if (G == 2 && grp == 1) named_arrive(3, 2 * T);   // group 0 takes the first turn in phase 1
+    if (G > 1 && grp == G - 1) named_arrive(8, 2 * T);   // group 0 takes the first turn in phase 1
     int p = blockIdx.x + grp * gridDim.x;
     if (tid == 0 && p < a.n_patches) {
         mbar_expect_tx(&mbar[0], a.stride);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
         }
 
         // ---- (c) phase 1: element contraction (the two groups alternate here)
-        if (G == 2) named_sync(3 + grp, 2 * T);
+        if (G > 1) named_sync(8 + grp, 2 * T);
         const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
         if (tid < ne) {
             const uint16_t *lc = reinterpret_cast<const uint16_t *>(bl + a.off_lc);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
             if (!ok) atomicOr(a.fail, 1);
         }
         if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 3] = clock64();
-        if (G == 2) named_arrive(3 + (grp ^ 1), 2 * T);
+        if (G > 1) named_arrive(8 + (grp + 1) % G, 2 * T);
         if (G == 1) __syncthreads(); else named_sync(1 + grp, T);
         if (a.timing && blockIdx.x == 0 && threadIdx.x == 0 && it < 8) a.timing[it * 8 + 4] = clock64();
 
@@ -342,7 +342,7 @@ int ensure_built(jfem_handle *h) {
     JFEM_TRY(h->e2i.upload(e2i));
     JFEM_TRY(h->iptr.upload(h->hif.iptr));
     JFEM_TRY(h->islots.upload(h->hif.islots));
-    JFEM_TRY(h->ipart.alloc((size_t)3 * h->hif.n_partials));
+    JFEM_TRY(h->ipart.alloc((size_t)3 * h->hif.n_partials + 3));
     JFEM_TRY(h->coords.upload(h->mesh.coords));
     JFEM_TRY(h->dflags.alloc(4));
     JFEM_CUDA(cudaMemset(h->dflags.p, 0, 4 * sizeof(int)));
@@ -363,12 +363,12 @@ int ensure_built(jfem_handle *h) {
 template <int NNPE, int CLS, int MODE, class Pt, int T>
 static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const Pt &pt) {
     constexpr int NF = Pt::NF;
-    constexpr int G = (PatchCfg<NNPE, CLS, MODE>::fast && T <= 256) ? 2 : 1;
+    constexpr int G = !PatchCfg<NNPE, CLS, MODE>::fast ? 1 : (T == 128 ? 3 : (T == 256 ? 2 : 1));
     size_t gsm = 16 + 2 * (size_t)D.stride + sizeof(double) * (3 * (NNPE * T + 5) + 1 + (size_t)3 * D.max_nodes * (NF == 2 ? 2 : 1) + (size_t)3 * D.max_nx);
     gsm = (gsm + 127) & ~(size_t)127;
     a.group_smem = (int)gsm;
     size_t smem = gsm * G;
-    if (G == 2 && smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
+    if (G > 1 && smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
     auto kern = patch_kernel<NNPE, CLS, MODE, Pt, T, G>;
     static size_t configured = 0;
     if (smem > configured) {
