@@ -125,6 +125,8 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
     } else if (!strcmp(key, "debug_timing")) {
         if (value != 0) { JFEM_TRY(h->timing.alloc(64)); JFEM_CUDA(cudaMemset(h->timing.p, 0, 64 * sizeof(long long))); }
         else h->timing.release();
+    } else if (!strcmp(key, "warp_specialised")) {
+        h->warp_specialised = value != 0;
     } else if (!strcmp(key, "deterministic")) {
         h->deterministic = value != 0;
     } else if (!strcmp(key, "affine_fast_path")) {

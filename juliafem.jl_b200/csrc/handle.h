@@ -18,7 +18,7 @@ struct jfem_handle {
     MeshHost mesh;
     // options
     int patch_elems = 256;
-    bool deterministic = true, affine = true;
+    bool deterministic = true, affine = true, warp_specialised = true;
     // material
     int mat_kind = -1;
     double mat[4] = {0, 0, 0, 0};

@@ -90,18 +90,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int T, int NF>
 __device__ __forceinline__ void patch_gather_async(const PatchKArgs &a, const unsigned char *bl, int tid, double *xs, double *Xs, double *us) {
     const int *hdr = reinterpret_cast<const int *>(bl);
-    const int n3 = 3 * hdr[0], nx3 = 3 * (int)((unsigned)hdr[1] >> 16);
+    const int np = hdr[0], nx = (int)((unsigned)hdr[1] >> 16);
     const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
     const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
-    for (int i = tid; i < n3; i += T) {
-        const int j = i / 3;
-        const long long g = 3 * (long long)(pn[j] & PN_ID_MASK) + (i - 3 * j);
-        cp_async8(xs + i, a.x + g);
-        if (NF == 2) cp_async8(us + i, a.ulin + g);
+    for (int j = tid; j < np; j += T) {   // one node (3 x 8-byte copies) per thread: few instructions per copy
+        const long long g = 3 * (long long)(pn[j] & PN_ID_MASK);
+        cp_async8(xs + 3 * j, a.x + g); cp_async8(xs + 3 * j + 1, a.x + g + 1); cp_async8(xs + 3 * j + 2, a.x + g + 2);
+        if (NF == 2) { cp_async8(us + 3 * j, a.ulin + g); cp_async8(us + 3 * j + 1, a.ulin + g + 1); cp_async8(us + 3 * j + 2, a.ulin + g + 2); }
     }
-    for (int i = tid; i < nx3; i += T) {
-        const int j = i / 3;
-        cp_async8(Xs + i, a.coords + 3 * (long long)xl[j] + (i - 3 * j));
+    for (int j = tid; j < nx; j += T) {
+        const long long g = 3 * (long long)xl[j];
+        cp_async8(Xs + 3 * j, a.coords + g); cp_async8(Xs + 3 * j + 1, a.coords + g + 1); cp_async8(Xs + 3 * j + 2, a.coords + g + 2);
     }
     cp_async_commit();
 }
@@ -247,6 +246,171 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant for the headline case (affine Tet10, linear elastic): one persistent block per SM with
+//   * 8 COMPUTE warps (256 threads, registers raised with setmaxnreg): phase 1 of patch i, back to back
+//   * 12 HELPER warps (384 threads, registers lowered): asynchronous gather of patch i+1 and the per-node reduction +
+//     stores of patch i-1, concurrently with the compute warps
+// so the fp64 pipe never waits for the LSU-bound phases.  Hand-off through mbarriers (full/empty pairs on the double
+// buffered x tile and staging tile); metadata blobs triple-buffered by TMA bulk copies.
+// ------------------------------------------------------------------------------------------------------------------
+#define WS_T 256
+#define WS_H 384
+#define WS_COMPUTE_REGS 152   // 256*152 + 384*56 <= 640*96 (the pool setmaxnreg redistributes is the launch allocation)
+#define WS_HELPER_REGS 56
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct WsSmem {   // byte offsets inside dynamic shared memory, computed on the host
+    int blob, stage, xs, Xs, total;
+};
+
+template <class Pt>
+__global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, Pt pt, WsSmem L) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    if (a.done && *a.done) return;
+    constexpr int NNPE = 10, T = WS_T, PS = NNPE * T + 5;
+    uint64_t *mb = reinterpret_cast<uint64_t *>(sm);
+    uint64_t *blob_full = mb, *xs_full = mb + 3, *xs_empty = mb + 5, *stage_full = mb + 7, *stage_empty = mb + 9;
+    unsigned char *blobs = sm + L.blob;
+    const size_t stage_sz = 3 * PS + 1;
+    double *stage0 = reinterpret_cast<double *>(sm + L.stage);
+    double *xs0 = reinterpret_cast<double *>(sm + L.xs);
+    double *Xs0 = reinterpret_cast<double *>(sm + L.Xs);
+    const int xs_sz = 3 * a.max_nodes, Xs_sz = 3 * a.max_nx;
+    const int n_it = (a.n_patches - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; k++) mbar_init(&blob_full[k], 1);
+        for (int k = 0; k < 2; k++) {
+            mbar_init(&xs_full[k], WS_H); mbar_init(&xs_empty[k], WS_T);
+            mbar_init(&stage_full[k], WS_T); mbar_init(&stage_empty[k], WS_H);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (threadIdx.x < WS_T) {
+        // =========================== compute warps ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_COMPUTE_REGS));
+        const int tid = threadIdx.x;
+        for (int i = 0; i < n_it; i++) {
+            const int p = blockIdx.x + i * gridDim.x;
+            const unsigned char *bl = blobs + (size_t)(i % 3) * a.stride;
+            double *stage = stage0 + (size_t)(i & 1) * stage_sz;
+            const double *xs = xs0 + (size_t)(i & 1) * xs_sz, *Xs = Xs0 + (size_t)(i & 1) * Xs_sz;
+            mbar_wait(&blob_full[i % 3], (i / 3) & 1);
+            mbar_wait(&xs_full[i & 1], (i >> 1) & 1);
+            if (i >= 2) mbar_wait(&stage_empty[i & 1], ((i >> 1) - 1) & 1);
+            const int ne = reinterpret_cast<const int *>(bl)[3];
+            if (tid < ne) {
+                const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
+                const uint16_t *xsl = reinterpret_cast<const uint16_t *>(bl + a.off_xs);
+                const uint16_t *lc = reinterpret_cast<const uint16_t *>(bl + a.off_lc);
+                const uint8_t *rk = reinterpret_cast<const uint8_t *>(bl + a.off_gs);
+                int n[NNPE], nxs[4];
+                JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = lc[k * T + tid];
+                JF_UNROLL for (int k = 0; k < 4; k++) nxs[k] = xsl[n[k]];
+                auto out = [=](int k, double v0, double v1, double v2) {
+                    double *d = stage + go[n[k]] + rk[k * T + tid];
+                    d[0] = v0; d[PS] = v1; d[2 * PS] = v2;
+                };
+                SField U{xs, n};
+                SField X{Xs, nxs};
+                tet10_affine_linear(pt.la, pt.mu, U, X, out);
+            }
+            (void)p;
+            mbar_arrive(&xs_empty[i & 1]);
+            mbar_arrive(&stage_full[i & 1]);
+        }
+    } else {
+        // =========================== helper warps ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_HELPER_REGS));
+        const int hid = threadIdx.x - WS_T;
+        if (hid == 0)
+            for (int k = 0; k < 3 && k < n_it; k++) {
+                mbar_expect_tx(&blob_full[k], a.stride);
+                bulk_g2s(blobs + (size_t)k * a.stride, a.blob + (size_t)(blockIdx.x + k * gridDim.x) * a.stride, a.stride, &blob_full[k]);
+            }
+        for (int i = 0; i <= n_it; i++) {
+            if (i < n_it) {   // ---- gather patch i into x tile (i & 1)
+                const unsigned char *bl = blobs + (size_t)(i % 3) * a.stride;
+                mbar_wait(&blob_full[i % 3], (i / 3) & 1);
+                if (i >= 2) mbar_wait(&xs_empty[i & 1], ((i >> 1) - 1) & 1);
+                double *xs = xs0 + (size_t)(i & 1) * xs_sz, *Xs = Xs0 + (size_t)(i & 1) * Xs_sz;
+                const int *hdr = reinterpret_cast<const int *>(bl);
+                const int np = hdr[0], nx = (int)((unsigned)hdr[1] >> 16);
+                const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+                const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
+                for (int j = hid; j < np; j += WS_H) {
+                    const long long g = 3 * (long long)(pn[j] & PN_ID_MASK);
+                    cp_async8(xs + 3 * j, a.x + g); cp_async8(xs + 3 * j + 1, a.x + g + 1); cp_async8(xs + 3 * j + 2, a.x + g + 2);
+                }
+                for (int j = hid; j < nx; j += WS_H) {
+                    const long long g = 3 * (long long)xl[j];
+                    cp_async8(Xs + 3 * j, a.coords + g); cp_async8(Xs + 3 * j + 1, a.coords + g + 1); cp_async8(Xs + 3 * j + 2, a.coords + g + 2);
+                }
+                cp_async_mbar_arrive_noinc(&xs_full[i & 1]);   // arrives when this thread's copies have landed
+            }
+            if (i >= 1) {     // ---- reduce + store patch i-1
+                const int k = i - 1;
+                const unsigned char *bl = blobs + (size_t)(k % 3) * a.stride;
+                const double *stage = stage0 + (size_t)(k & 1) * stage_sz;
+                mbar_wait(&stage_full[k & 1], (k >> 1) & 1);
+                const int *hdr = reinterpret_cast<const int *>(bl);
+                const int np = hdr[0], nif = hdr[1] & 0xFFFF, ipb = hdr[2];
+                const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+                const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
+                for (int j = hid; j < np; j += WS_H) {
+                    const int q0 = go[j], cnt = go[j + 1] - q0;
+                    const double *sp = stage + q0;
+                    double s0 = 0, s1 = 0, s2 = 0;
+                    int q = 0;
+                    for (; q + 2 <= cnt; q += 2) {
+                        const double a0 = sp[q], a1 = sp[q + 1], b0 = sp[PS + q], b1 = sp[PS + q + 1], c0 = sp[2 * PS + q], c1 = sp[2 * PS + q + 1];
+                        s0 += a0; s1 += b0; s2 += c0;
+                        s0 += a1; s1 += b1; s2 += c1;
+                    }
+                    if (q < cnt) { s0 += sp[q]; s1 += sp[PS + q]; s2 += sp[2 * PS + q]; }
+                    const uint32_t w = pn[j];
+                    if (a.project) {
+                        if (w & (1u << PN_FIXSHIFT)) s0 = 0.0;
+                        if (w & (2u << PN_FIXSHIFT)) s1 = 0.0;
+                        if (w & (4u << PN_FIXSHIFT)) s2 = 0.0;
+                    }
+                    if (j < nif) {
+                        if (a.atomic_iface) {
+                            double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
+                            atomicAdd(py, s0); atomicAdd(py + 1, s1); atomicAdd(py + 2, s2);
+                        } else {
+                            double *pp = a.ipart + 3 * ((long long)ipb + j);
+                            pp[0] = s0; pp[1] = s1; pp[2] = s2;
+                        }
+                    } else {
+                        double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
+                        py[0] = s0; py[1] = s1; py[2] = s2;
+                    }
+                }
+                mbar_arrive(&stage_empty[k & 1]);
+                // blob buffer (k % 3) is free once every helper thread is past the reduction: refill it with patch k+3
+                if (k + 3 < n_it) {
+                    named_sync(1, WS_H);
+                    if (hid == 0) {
+                        mbar_expect_tx(&blob_full[k % 3], a.stride);
+                        bulk_g2s(blobs + (size_t)(k % 3) * a.stride, a.blob + (size_t)(blockIdx.x + (k + 3) * gridDim.x) * a.stride, a.stride,
+                                 &blob_full[k % 3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // y[interface node] = sum of its partial slots, ascending (set, patch) order.  3 threads per node; the first four
 // slots come from one 16-byte load (islot4), rarer nodes with more slots continue through the CSR list.
 __global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const int4 *__restrict__ islot4, const int32_t *__restrict__ iptr,
@@ -363,6 +527,32 @@ int ensure_built(jfem_handle *h) {
 template <int NNPE, int CLS, int MODE, class Pt, int T>
 static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const Pt &pt) {
     constexpr int NF = Pt::NF;
+    if constexpr (NNPE == 10 && CLS == CLASS_AFFINE && MODE == OP_LINEAR && T == WS_T) {
+        if (h->warp_specialised) {
+            constexpr int PS = NNPE * T + 5;
+            auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+            WsSmem L;
+            L.blob = 128;
+            L.stage = (int)r128(L.blob + 3 * (size_t)D.stride);
+            L.xs = (int)r128(L.stage + 2 * sizeof(double) * (3 * PS + 1));
+            L.Xs = (int)r128(L.xs + 2 * sizeof(double) * 3 * D.max_nodes);
+            L.total = (int)r128(L.Xs + 2 * sizeof(double) * 3 * D.max_nx);
+            if (L.total <= 227 * 1024) {
+                auto kws = patch_kernel_ws<Pt>;
+                static int configured_ws = 0;
+                if (L.total > configured_ws) {
+                    JFEM_CUDA(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+                    configured_ws = L.total;
+                }
+                h->last_smem = L.total; h->last_blocks_per_sm = 1;
+                int grid = h->n_sms < D.n_patches ? h->n_sms : D.n_patches;
+                kws<<<grid, WS_T + WS_H, L.total, h->stream>>>(a, pt, L);
+                JFEM_CUDA(cudaGetLastError());
+                h->matvec_launches++;
+                return JFEM_OK;
+            }
+        }
+    }
     constexpr int G = !PatchCfg<NNPE, CLS, MODE>::fast ? 1 : (T == 128 ? 3 : (T == 256 ? 2 : 1));
     size_t gsm = 16 + 2 * (size_t)D.stride + sizeof(double) * (3 * (NNPE * T + 5) + 1 + (size_t)3 * D.max_nodes * (NF == 2 ? 2 : 1) + (size_t)3 * D.max_nx);
     gsm = (gsm + 127) & ~(size_t)127;
