@@ -215,8 +215,6 @@ def main():
     for k in range(args.steps):
         if flush is not None:
             flush.fill_(float(k))
-        if world > 1:
-            dist.barrier()
         ev[k][0].record()
         step()
         ev[k][1].record()

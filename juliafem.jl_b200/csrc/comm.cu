@@ -13,6 +13,8 @@
 
 #include "handle.h"
 
+#define AR_WORDS 8    // all-reduce mailbox slot: sequence word + up to 7 values
+
 typedef struct { char internal[128]; } nccl_uid;
 typedef int (*fn_get_uid)(nccl_uid *);
 typedef int (*fn_init_rank)(ncclComm **, int, nccl_uid, int);
@@ -154,9 +156,10 @@ extern "C" int jfem_comm_p2p_export(jfem_handle *h, char *handles128) {
     if (nnb > 8) { jfem_set_error("p2p halo supports at most 8 neighbours"); return JFEM_EINVAL; }
     h->p2p_half = (size_t)3 * h->recv_ptr[nnb] + 8;
     JFEM_TRY(h->p2p_land.alloc(2 * h->p2p_half));
-    JFEM_TRY(h->p2p_flags.alloc(h->n_ranks + 1));
+    const size_t ctrl_words = (size_t)h->n_ranks + 1 + 2 * (size_t)h->n_ranks * AR_WORDS;   // halo flags + all-reduce mailboxes
+    JFEM_TRY(h->p2p_flags.alloc(ctrl_words));
     JFEM_TRY(h->p2p_ticket.alloc(1));
-    JFEM_CUDA(cudaMemset(h->p2p_flags.p, 0, (h->n_ranks + 1) * sizeof(unsigned long long)));
+    JFEM_CUDA(cudaMemset(h->p2p_flags.p, 0, ctrl_words * sizeof(unsigned long long)));
     JFEM_CUDA(cudaMemset(h->p2p_ticket.p, 0, sizeof(unsigned int)));
     cudaIpcMemHandle_t hl, hf;
     JFEM_CUDA(cudaIpcGetMemHandle(&hl, h->p2p_land.p));
@@ -190,11 +193,69 @@ extern "C" int jfem_comm_p2p_import(jfem_handle *h, const char *all_handles, con
         h->p2p_peer_off[i] = off;
         h->p2p_peer_half[i] = (size_t)halves[s];
     }
+    // control buffers of all ranks (all-reduce mailboxes)
+    h->p2p_ctrl.assign(h->n_ranks, nullptr);
+    for (int s = 0; s < h->n_ranks; s++) {
+        if (s == h->rank) { h->p2p_ctrl[s] = h->p2p_flags.p; continue; }
+        bool found = false;
+        for (int i = 0; i < nnb; i++)
+            if (h->nb_rank[i] == s) { h->p2p_ctrl[s] = h->p2p_peer_flag[i] - h->rank; found = true; }
+        if (found) continue;
+        cudaIpcMemHandle_t hf;
+        memcpy(&hf, all_handles + (size_t)s * 128 + 64, 64);
+        void *pf = nullptr;
+        JFEM_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_ctrl[s] = (unsigned long long *)pf;
+    }
     h->p2p_ready = true;
     return JFEM_OK;
 }
 
+// ---- all-reduce of a few doubles through the same IPC-mapped control buffers: every rank writes its partial sums into
+// its slot of every rank's mailbox (values, system fence, sequence word), then sums the n_ranks slots of its own
+// mailbox in RANK ORDER (deterministic, identical on all ranks).  One single-warp kernel, ~NVLink write latency,
+// instead of an NCCL all-reduce launch (~15-25 us for 8 bytes).
+
+struct P2PAllArgs {
+    int n_ranks, rank;
+    unsigned long long *ctrl[8];   // control buffer of every rank (own included)
+    long long mail_off;            // offset (u64 words) of the mailboxes inside a control buffer
+};
+
+__global__ void p2p_allreduce_kernel(P2PAllArgs a, double *sums, int count, unsigned long long seq) {
+    const int r = threadIdx.x;
+    const int par = (int)(seq & 1);
+    if (r < a.n_ranks) {
+        volatile unsigned long long *slot = a.ctrl[r] + a.mail_off + ((size_t)par * a.n_ranks + a.rank) * AR_WORDS;
+        for (int c = 0; c < count; c++) slot[1 + c] = (unsigned long long)__double_as_longlong(sums[c]);
+        __threadfence_system();
+        slot[0] = seq;
+        volatile unsigned long long *mine = a.ctrl[a.rank] + a.mail_off + ((size_t)par * a.n_ranks + r) * AR_WORDS;
+        while (mine[0] != seq) { }
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (r < count) {
+        double acc = 0.0;
+        for (int q = 0; q < a.n_ranks; q++) {
+            volatile unsigned long long *mine = a.ctrl[a.rank] + a.mail_off + ((size_t)par * a.n_ranks + q) * AR_WORDS;
+            acc += __longlong_as_double((long long)mine[1 + r]);
+        }
+        sums[r] = acc;
+    }
+}
+
 int comm_allreduce_sum(jfem_handle *h, double *buf, int count) {
+    if (h->p2p_ready && h->n_ranks <= 8 && count < AR_WORDS) {
+        P2PAllArgs a;
+        a.n_ranks = h->n_ranks; a.rank = h->rank; a.mail_off = h->n_ranks + 1;
+        for (int r = 0; r < h->n_ranks; r++) a.ctrl[r] = h->p2p_ctrl[r];
+        h->p2p_ar_seq++;
+        p2p_allreduce_kernel<<<1, 32, 0, h->stream>>>(a, buf, count, h->p2p_ar_seq);
+        JFEM_CUDA(cudaGetLastError());
+        h->total_launches++;
+        return JFEM_OK;
+    }
     JFEM_NCCL(N.allreduce(buf, buf, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->comm, h->stream));
     return JFEM_OK;
 }

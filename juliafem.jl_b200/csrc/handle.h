@@ -76,7 +76,8 @@ struct jfem_handle {
     DevBuf<unsigned long long> p2p_flags;
     DevBuf<unsigned int> p2p_ticket;
     std::vector<double *> p2p_peer_land;
-    std::vector<unsigned long long *> p2p_peer_flag;
+    std::vector<unsigned long long *> p2p_peer_flag, p2p_ctrl;
+    unsigned long long p2p_ar_seq = 0;
     std::vector<int64_t> p2p_peer_off;
     std::vector<size_t> p2p_peer_half;
     // stats
