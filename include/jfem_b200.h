@@ -56,7 +56,7 @@ extern "C" {
 #define JFEM_PROJECT 1      /* zero Dirichlet rows of the result (apply_dirichlet_kernel!, ext:423-435) */
 #define JFEM_TANGENT 2      /* operator = tangent K(u_lin) incl. geometric stiffness, not the linear-elastic K */
 #define JFEM_USE_CSR 4      /* CG / matvec through the assembled CSR matrix (cpu:221-254) instead of matrix-free */
-#define JFEM_JACOBI 8       /* opt-in 3x3 block-Jacobi preconditioner (not in the reference) */
+#define JFEM_JACOBI 8       /* opt-in 3x3 block-Jacobi preconditioned CG (not in the reference, which lists it as the first missing piece) */
 
 typedef struct jfem_handle jfem_handle;
 

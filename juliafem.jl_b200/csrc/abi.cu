@@ -390,7 +390,6 @@ int jfem_cg(jfem_handle *h, const double *b, double *x, double tol, int tol_is_r
             double *resid, int on_device) {
     CHECK_H(h);
     if (!b || !x) { jfem_set_error("jfem_cg: null vector"); return JFEM_EINVAL; }
-    if (flags & JFEM_JACOBI) return jacobi_build(h, flags);
     JFEM_TRY(ensure_built(h));
     const double *db; double *dx;
     JFEM_TRY(in_vec(h, b, on_device, h->wy, &db));

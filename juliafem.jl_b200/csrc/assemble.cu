@@ -140,6 +140,49 @@ __global__ void __launch_bounds__(256) spmv_kernel(long long n_rows, const long 
 
 // ------------------------------------------------------------------------------------------------ host side
 
+// greedy element colouring (src/preprocess.jl:331-398), elements visited in ascending id; elements of one colour share no node
+int ensure_colouring(jfem_handle *h) {
+    if (!h->colour_ptr.empty()) return JFEM_OK;
+    const MeshHost &m = h->mesh;
+    const int nnpe = m.nnpe;
+    const int64_t nn = m.n_nodes, ne = m.n_elems;
+    std::vector<int64_t> nptr(nn + 1, 0);
+    for (int64_t i = 0; i < ne * nnpe; i++) nptr[m.conn[i] + 1]++;
+    for (int64_t i = 0; i < nn; i++) nptr[i + 1] += nptr[i];
+    std::vector<int32_t> n2e(nptr[nn]);
+    {
+        std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
+        for (int64_t e = 0; e < ne; e++) for (int k = 0; k < nnpe; k++) n2e[fill[m.conn[e * nnpe + k]]++] = (int32_t)e;
+    }
+    std::vector<int32_t> colour(ne, -1);
+    int ncol = 0;
+    {
+        std::vector<uint8_t> used;
+        for (int64_t e = 0; e < ne; e++) {
+            used.assign(ncol + 1, 0);
+            for (int k = 0; k < nnpe; k++) {
+                const int32_t a = m.conn[e * nnpe + k];
+                for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) { int32_t c = colour[n2e[q]]; if (c >= 0) used[c] = 1; }
+            }
+            int c = 0;
+            while (used[c]) c++;
+            colour[e] = c;
+            if (c + 1 > ncol) ncol = c + 1;
+        }
+    }
+    h->colour_ptr.assign(ncol + 1, 0);
+    for (int64_t e = 0; e < ne; e++) h->colour_ptr[colour[e] + 1]++;
+    for (int c = 0; c < ncol; c++) h->colour_ptr[c + 1] += h->colour_ptr[c];
+    std::vector<int32_t> celems(ne);
+    {
+        std::vector<int64_t> fill(h->colour_ptr.begin(), h->colour_ptr.end() - 1);
+        for (int64_t e = 0; e < ne; e++) celems[fill[colour[e]]++] = (int32_t)e;
+    }
+    JFEM_TRY(h->colour_elems.upload(celems));
+    if (h->dconn.n == 0) JFEM_TRY(h->dconn.upload(m.conn));
+    return JFEM_OK;
+}
+
 int csr_build(jfem_handle *h) {
     if (h->csr_built) return JFEM_OK;
     JFEM_TRY(ensure_built(h));
@@ -186,36 +229,10 @@ int csr_build(jfem_handle *h) {
             for (int l = 0; l < nnpe; l++)
                 eblk[(e * nnpe + k) * nnpe + l] = (uint16_t)(std::lower_bound(lo, hi, m.conn[e * nnpe + l]) - lo);
         }
-    // greedy colouring (src/preprocess.jl:331-398), elements visited in ascending id
-    std::vector<int32_t> colour(ne, -1);
-    int ncol = 0;
-    {
-        std::vector<uint8_t> used;
-        for (int64_t e = 0; e < ne; e++) {
-            used.assign(ncol + 1, 0);
-            for (int k = 0; k < nnpe; k++) {
-                const int32_t a = m.conn[e * nnpe + k];
-                for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) { int32_t c = colour[n2e[q]]; if (c >= 0) used[c] = 1; }
-            }
-            int c = 0;
-            while (used[c]) c++;
-            colour[e] = c;
-            if (c + 1 > ncol) ncol = c + 1;
-        }
-    }
-    h->colour_ptr.assign(ncol + 1, 0);
-    for (int64_t e = 0; e < ne; e++) h->colour_ptr[colour[e] + 1]++;
-    for (int c = 0; c < ncol; c++) h->colour_ptr[c + 1] += h->colour_ptr[c];
-    std::vector<int32_t> celems(ne);
-    {
-        std::vector<int64_t> fill(h->colour_ptr.begin(), h->colour_ptr.end() - 1);
-        for (int64_t e = 0; e < ne; e++) celems[fill[colour[e]]++] = (int32_t)e;
-    }
+    JFEM_TRY(ensure_colouring(h));
     JFEM_TRY(h->nadj_ptr.upload(ap));
     JFEM_TRY(h->nadj.upload(adj));
     JFEM_TRY(h->eblk.upload(eblk));
-    JFEM_TRY(h->colour_elems.upload(celems));
-    JFEM_TRY(h->dconn.upload(m.conn));
     const int64_t nnz = 9 * ap[nn];
     JFEM_TRY(h->rowptr.alloc(3 * nn + 1));
     JFEM_TRY(h->colind.alloc(nnz));
@@ -349,9 +366,91 @@ int element_matrices(jfem_handle *h, const double *u, int64_t e0, int64_t ne, do
     return check_fail(h, "element integration");
 }
 
+// 3x3 diagonal blocks of K (or of the tangent K(u)) without assembling K: one thread per (element, node k) evaluates the
+// three columns (k, 0..2) of the element matrix and keeps the rows of node k; coloured launches -> race-free, ordered.
+template <int NNPE, class Pt>
+__global__ void __launch_bounds__(128) elem_diag_kernel(AsmArgs a, Pt pt, double *__restrict__ D) {
+    constexpr int NF = Pt::NF;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.ne * NNPE) return;
+    const long long i = idx / NNPE;
+    const int kj = (int)(idx - i * NNPE);
+    const long long e = a.elems[a.e0 + i];
+    int n[NNPE];
+    JF_UNROLL for (int k = 0; k < NNPE; k++) n[k] = a.conn[e * NNPE + k];
+    AField X{a.coords, n, 0, 0};
+    double *d = D + 9LL * n[kj];
+    for (int cj = 0; cj < 3; cj++) {
+        AField F[NF];
+        F[0] = AField{nullptr, n, kj, cj};
+        if (NF == 2) F[NF - 1] = AField{a.u, n, 0, 0};
+        auto out = [=](int k, double v0, double v1, double v2) {
+            if (k == kj) { d[cj] += v0; d[3 + cj] += v1; d[6 + cj] += v2; }
+        };
+        elem_dispatch<NNPE>(pt, a.e2i[e], F, X, out);
+    }
+}
+
+// D <- inverse of the projected block (fixed dofs: unit row/column)
+__global__ void invert_blocks_kernel(long long n_nodes, const uint8_t *__restrict__ fixed, double *__restrict__ D) {
+    long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_nodes) return;
+    double A[3][3], B[3][3];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[r][c] = D[9 * n + 3 * r + c];
+    for (int r = 0; r < 3; r++)
+        if (fixed[3 * n + r]) { for (int c = 0; c < 3; c++) { A[r][c] = 0.0; A[c][r] = 0.0; } A[r][r] = 1.0; }
+    const double tr = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+    if (tr == 0.0) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) B[r][c] = (r == c) ? 1.0 : 0.0; }   // orphan node
+    else inv3x3(A, B);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) D[9 * n + 3 * r + c] = B[r][c];
+}
+
+template <int NNPE, class Pt>
+static int launch_diag(jfem_handle *h, AsmArgs a, const Pt &pt, double *D) {
+    const long long nthreads = a.ne * NNPE;
+    if (nthreads == 0) return JFEM_OK;
+    elem_diag_kernel<NNPE, Pt><<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(a, pt, D);
+    JFEM_CUDA(cudaGetLastError());
+    h->total_launches++;
+    return JFEM_OK;
+}
+
+template <int NNPE>
+static int diag_by_material(jfem_handle *h, AsmArgs a, double *D, bool tangent) {
+    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
+    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
+    const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || !tangent) { PtLinear pt; pt.la = la; pt.mu = mu; return launch_diag<NNPE>(h, a, pt, D); }
+    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; pt.la = la; pt.mu = mu; return launch_diag<NNPE>(h, a, pt, D); }
+    PtPPTangent pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.n_gp = n_gp;
+    return launch_diag<NNPE>(h, a, pt, D);
+}
+
+// opt-in block-Jacobi preconditioner (the reference lists a preconditioner as its first missing piece,
+// docs/src/book/gpu_benchmark_milestone.md:561-565): cg_dinv = inverse 3x3 diagonal blocks of the (projected) operator
 int jacobi_build(jfem_handle *h, int flags) {
-    (void)flags;
-    jfem_set_error("JFEM_JACOBI preconditioner is not implemented in this build");
-    (void)h;
-    return JFEM_EINVAL;
+    JFEM_TRY(ensure_built(h));
+    JFEM_TRY(ensure_colouring(h));
+    const bool tangent = (flags & JFEM_TANGENT) != 0;
+    const size_t n9 = 9 * (size_t)h->mesh.n_nodes;
+    if (h->cg_dinv.n != n9) JFEM_TRY(h->cg_dinv.alloc(n9));
+    JFEM_CUDA(cudaMemsetAsync(h->cg_dinv.p, 0, n9 * sizeof(double), h->stream));
+    AsmArgs a;
+    a.conn = h->dconn.p; a.elems = h->colour_elems.p; a.coords = h->coords.p; a.u = h->ulin.p; a.e2i = (const long long *)h->e2i.p;
+    a.adjptr = nullptr; a.eblk = nullptr; a.vals = nullptr; a.Ke = nullptr; a.fail = h->dflags.p;
+    for (size_t c = 0; c + 1 < h->colour_ptr.size(); c++) {
+        a.e0 = h->colour_ptr[c]; a.ne = h->colour_ptr[c + 1] - h->colour_ptr[c];
+        int rc;
+        switch (h->mesh.nnpe) {
+            case 10: rc = diag_by_material<10>(h, a, h->cg_dinv.p, tangent); break;
+            case 8: rc = diag_by_material<8>(h, a, h->cg_dinv.p, tangent); break;
+            default: rc = diag_by_material<4>(h, a, h->cg_dinv.p, tangent); break;
+        }
+        JFEM_TRY(rc);
+    }
+    const long long nn = h->mesh.n_nodes;
+    invert_blocks_kernel<<<(unsigned)((nn + 127) / 128), 128, 0, h->stream>>>(nn, h->fixed.p, h->cg_dinv.p);
+    JFEM_CUDA(cudaGetLastError());
+    h->total_launches++;
+    return JFEM_OK;
 }

@@ -56,7 +56,7 @@ __device__ __forceinline__ bool grid_sum(const double (&v)[N], double *partials,
     return threadIdx.x == 0;
 }
 
-enum { ST_INIT = 0, ST_ALPHA = 1, ST_UPDATE = 2 };
+enum { ST_INIT = 0, ST_ALPHA = 1, ST_UPDATE = 2, ST_ZINIT = 3, ST_Z = 4 };
 
 // scalar stage logic, run by exactly one thread once the (global) sums are known
 __device__ __forceinline__ void cg_scalar_step(CGScalars *s, int stage) {
@@ -68,13 +68,18 @@ __device__ __forceinline__ void cg_scalar_step(CGScalars *s, int stage) {
         s->done = (s->rel ? rn <= s->thr : rn < s->thr) ? 1 : 0;   // early exit, cpu.jl:230-233
         if (s->max_iter <= 0) s->done = 1;
     } else if (stage == ST_ALPHA) {
-        s->alpha = s->rr / s->pAp;
-    } else {
+        s->alpha = (s->pcg ? s->rz : s->rr) / s->pAp;
+    } else if (stage == ST_UPDATE) {
         double rn = sqrt(s->rr_new);
         s->iters += 1;
-        s->beta = s->rr_new / s->rr;
+        if (!s->pcg) s->beta = s->rr_new / s->rr;
         s->rr = s->rr_new;
         if ((s->rel ? rn <= s->thr : rn < s->thr) || s->iters >= s->max_iter) s->done = 1;
+    } else if (stage == ST_ZINIT) {
+        s->rz = s->rz_new;
+    } else {   // ST_Z: preconditioned beta = (r.z)_new / (r.z)_old
+        s->beta = s->rz_new / s->rz;
+        s->rz = s->rz_new;
     }
 }
 
@@ -82,7 +87,8 @@ __global__ void cg_scalar_kernel(CGScalars *s, int stage, const double *sums) {
     if (stage != ST_INIT && s->done) return;
     if (stage == ST_INIT) { s->rr_new = sums[0]; s->bnorm2 = sums[1]; }
     else if (stage == ST_ALPHA) s->pAp = sums[0];
-    else s->rr_new = sums[0];
+    else if (stage == ST_UPDATE) s->rr_new = sums[0];
+    else s->rz_new = sums[0];
     cg_scalar_step(s, stage);
 }
 
@@ -138,6 +144,27 @@ __global__ void __launch_bounds__(RED_THREADS) cg_update_kernel(long long n_all,
     }
 }
 
+// z = Dinv r (3x3 block per node), rz = r.z ; at init also p = z.  One thread per owned node.
+__global__ void __launch_bounds__(RED_THREADS) pcg_z_kernel(long long n_nodes, const double *__restrict__ r, const double *__restrict__ dinv,
+                                                             double *__restrict__ z, double *__restrict__ p, double *partials, CGScalars *s,
+                                                             double *sums, int fuse, int stage) {
+    if (stage == ST_Z && s->done) return;
+    double acc = 0;
+    for (long long n = (long long)blockIdx.x * RED_THREADS + threadIdx.x; n < n_nodes; n += (long long)gridDim.x * RED_THREADS) {
+        const double r0 = r[3 * n], r1 = r[3 * n + 1], r2 = r[3 * n + 2];
+        const double *d = dinv + 9 * n;
+        const double z0 = d[0] * r0 + d[1] * r1 + d[2] * r2, z1 = d[3] * r0 + d[4] * r1 + d[5] * r2, z2 = d[6] * r0 + d[7] * r1 + d[8] * r2;
+        z[3 * n] = z0; z[3 * n + 1] = z1; z[3 * n + 2] = z2;
+        if (stage == ST_ZINIT) { p[3 * n] = z0; p[3 * n + 1] = z1; p[3 * n + 2] = z2; }
+        acc += r0 * z0 + r1 * z1 + r2 * z2;
+    }
+    double v[1] = {acc}, t[1];
+    if (grid_sum<1>(v, partials, 0, &s->ticket[0], t)) {
+        sums[0] = t[0];
+        if (fuse) { s->rz_new = t[0]; cg_scalar_step(s, stage); }
+    }
+}
+
 // p = r + beta p  (skipped once converged: the reference returns before this update, cpu.jl:244-246)
 __global__ void cg_p_kernel(long long n, double *__restrict__ p, const double *__restrict__ r, const CGScalars *s) {
     if (s->done) return;
@@ -166,6 +193,7 @@ static int ensure_cg_buffers(jfem_handle *h) {
     if (h->cg_r.n != n) {
         JFEM_TRY(h->cg_r.alloc(n)); JFEM_TRY(h->cg_p.alloc(n)); JFEM_TRY(h->cg_Ap.alloc(n));
     }
+    if (h->cg_z.n != n) JFEM_TRY(h->cg_z.alloc(n));
     if (h->red_partials.n == 0) {
         JFEM_TRY(h->red_partials.alloc(4 * RED_BLOCKS + 8));
         JFEM_TRY(h->cg_s.alloc(1));
@@ -207,6 +235,10 @@ int cg_solve(jfem_handle *h, const double *b, double *x, double tol, int rel, in
     CGScalars init;
     memset(&init, 0, sizeof init);
     init.thr = tol; init.rel = rel; init.max_iter = max_iter;
+    const int pcg = (flags & JFEM_JACOBI) ? 1 : 0;
+    init.pcg = pcg;
+    if (pcg) JFEM_TRY(jacobi_build(h, flags));
+    const long long nn_own = n_own / 3;
     JFEM_CUDA(cudaMemcpyAsync(s, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
     // r0 = P(b - A x0)
     JFEM_TRY(apply_operator(h, flags, x, h->cg_Ap.p, nullptr));
@@ -219,6 +251,10 @@ int cg_solve(jfem_handle *h, const double *b, double *x, double tol, int rel, in
     if (!fuse) {
         JFEM_TRY(allreduce_sums(h, sums, 2));
         cg_scalar_kernel<<<1, 1, 0, h->stream>>>(s, ST_INIT, sums);
+    }
+    if (pcg) {
+        pcg_z_kernel<<<RED_BLOCKS, RED_THREADS, 0, h->stream>>>(nn_own, h->cg_r.p, h->cg_dinv.p, h->cg_z.p, h->cg_p.p, h->red_partials.p, s, sums, fuse, ST_ZINIT);
+        if (!fuse) { JFEM_TRY(allreduce_sums(h, sums, 1)); cg_scalar_kernel<<<1, 1, 0, h->stream>>>(s, ST_ZINIT, sums); }
     }
     h->total_launches += 2;
     int host_state[2] = {0, 0};   // iters, done
@@ -234,8 +270,12 @@ int cg_solve(jfem_handle *h, const double *b, double *x, double tol, int rel, in
             if (!fuse) { JFEM_TRY(allreduce_sums(h, sums, 1)); cg_scalar_kernel<<<1, 1, 0, h->stream>>>(s, ST_ALPHA, sums); }
             cg_update_kernel<<<RED_BLOCKS, RED_THREADS, 0, h->stream>>>(n_own, n_own, x, h->cg_r.p, h->cg_p.p, h->cg_Ap.p, h->red_partials.p, s, sums, fuse);
             if (!fuse) { JFEM_TRY(allreduce_sums(h, sums, 1)); cg_scalar_kernel<<<1, 1, 0, h->stream>>>(s, ST_UPDATE, sums); }
-            cg_p_kernel<<<RED_BLOCKS, RED_THREADS, 0, h->stream>>>(n_own, h->cg_p.p, h->cg_r.p, s);
-            h->total_launches += fuse ? 3 : 5;
+            if (pcg) {
+                pcg_z_kernel<<<RED_BLOCKS, RED_THREADS, 0, h->stream>>>(nn_own, h->cg_r.p, h->cg_dinv.p, h->cg_z.p, h->cg_p.p, h->red_partials.p, s, sums, fuse, ST_Z);
+                if (!fuse) { JFEM_TRY(allreduce_sums(h, sums, 1)); cg_scalar_kernel<<<1, 1, 0, h->stream>>>(s, ST_Z, sums); }
+            }
+            cg_p_kernel<<<RED_BLOCKS, RED_THREADS, 0, h->stream>>>(n_own, h->cg_p.p, pcg ? h->cg_z.p : h->cg_r.p, s);
+            h->total_launches += (fuse ? 3 : 5) + (pcg ? (fuse ? 1 : 2) : 0);
         }
         JFEM_CUDA(cudaGetLastError());
         launched += todo;

@@ -7,6 +7,7 @@ struct ncclComm;
 struct CGScalars {        // lives on the device; read by every CG kernel
     double rr, pAp, alpha, beta, rr_new, bnorm2, thr, rz, rz_new;
     int iters, done, max_iter, rel;
+    int pcg, pad_[3];
     unsigned int ticket[4];
 };
 
@@ -103,6 +104,7 @@ int newton_krylov(jfem_handle *h, const double *fext_dev, double *u_dev, double 
                   double *history, int history_cap);
 int vec_dot(jfem_handle *h, const double *a, const double *b, double *out_host);
 
+int ensure_colouring(jfem_handle *h);
 int csr_build(jfem_handle *h);
 int csr_assemble(jfem_handle *h, const double *u_dev, int symmetrise);
 int csr_fint(jfem_handle *h, const double *u_dev, double *f_dev);

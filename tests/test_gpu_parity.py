@@ -325,3 +325,20 @@ def test_newton_krylov_neo_hookean(L, oracle, jf):
     R[fixed - 1] = 0
     assert np.linalg.norm(R) < 1e-5
     assert np.abs(u).max() > 1e-3 and np.all(u[fixed - 1] == 0)
+
+
+def test_block_jacobi_pcg(L, oracle, jf):
+    """Opt-in 3x3 block-Jacobi PCG: same solution as plain CG, diagonal blocks equal the assembled ones."""
+    m = curved_tet10(jf.mesh, 8, 2, 2, amp=0.01)
+    fixed = jf.mesh.clamp_dofs(m, tol=0.02)
+    b = np.zeros(m.n_dofs); b[2::3] = -1e3
+    h = make(L, m)
+    h.set_dirichlet(fixed)
+    x0, it0, _ = h.cg(b, tol=1e-9, relative=True, max_iter=50000)
+    x1, it1, r1 = h.cg(b, tol=1e-9, relative=True, max_iter=50000, flags=L.JACOBI)
+    assert it1 < 50000 and it1 <= it0
+    assert relerr(x1, x0) < 1e-6 and np.all(x1[fixed - 1] == 0)
+    rp, ci, vals, _ = oracle.assemble_csr(10, m.coords, m.conn, par=LE)
+    r = b - oracle.spmv(rp, ci, vals, x1); r[fixed - 1] = 0
+    bn = b.copy(); bn[fixed - 1] = 0
+    assert np.linalg.norm(r) <= 5e-9 * np.linalg.norm(bn)
