@@ -123,7 +123,7 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         if (v != 128 && v != 256 && v != 512) { jfem_set_error("patch_elems must be 128, 256 or 512"); return JFEM_EINVAL; }
         if (v != h->patch_elems) { h->patch_elems = v; h->built = false; }
     } else if (!strcmp(key, "debug_timing")) {
-        if (value != 0) { JFEM_TRY(h->timing.alloc(64)); JFEM_CUDA(cudaMemset(h->timing.p, 0, 64 * sizeof(long long))); }
+        if (value != 0) { JFEM_TRY(h->timing.alloc(128)); JFEM_CUDA(cudaMemset(h->timing.p, 0, 128 * sizeof(long long))); }
         else h->timing.release();
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
@@ -219,7 +219,7 @@ int jfem_debug_timing(jfem_handle *h, long long *out64) {   /* not part of the p
     CHECK_H(h);
     if (!h->timing.p) { jfem_set_error("debug_timing option is off"); return JFEM_ESTATE; }
     JFEM_CUDA(cudaStreamSynchronize(h->stream));
-    JFEM_CUDA(cudaMemcpy(out64, h->timing.p, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+    JFEM_CUDA(cudaMemcpy(out64, h->timing.p, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
     return JFEM_OK;
 }
 

@@ -256,27 +256,32 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
 // ------------------------------------------------------------------------------------------------------------------
 #define WS_T 256
 #define WS_H 384
-#define WS_COMPUTE_REGS 152   // 256*152 + 384*56 <= 640*96 (the pool setmaxnreg redistributes is the launch allocation)
-#define WS_HELPER_REGS 56
+#define WS_NB 4             // metadata blob ring (TMA), refilled two patches ahead of first use
+#define WS_COMPUTE_REGS 168 // 256*168 + 384*48 <= 640*96: setmaxnreg redistributes the launch allocation, it cannot grow it
+#define WS_HELPER_REGS 48
+#define WS_GX 9             // flat x items per compute thread held in registers by the look-ahead gather (768 nodes)
+#define WS_GC 2             // flat coordinate items per compute thread
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 struct WsSmem {   // byte offsets inside dynamic shared memory, computed on the host
     int blob, stage, xs, Xs, total;
 };
 
+// COMPUTE warps, per patch i:  issue the global loads of patch i+1's x / coordinates into registers (coalesced LDG: the
+// patch node lists are id-sorted) -> phase 1 of patch i out of the x tile (i & 1) into staging tile (i & 1) -> signal the
+// helpers -> park the prefetched registers in x tile ((i+1) & 1).  The load latency hides behind phase 1.
+// HELPER warps, per patch k: wait for staging tile (k & 1) -> ordered per-node reduction + stores -> release the tile ->
+// refill blob slot (k % WS_NB) with patch k + WS_NB by one TMA bulk copy.
 template <class Pt>
 __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, Pt pt, WsSmem L) {
     extern __shared__ __align__(128) unsigned char sm[];
     if (a.done && *a.done) return;
     constexpr int NNPE = 10, T = WS_T, PS = NNPE * T + 5;
     uint64_t *mb = reinterpret_cast<uint64_t *>(sm);
-    uint64_t *blob_full = mb, *xs_full = mb + 3, *xs_empty = mb + 5, *stage_full = mb + 7, *stage_empty = mb + 9;
+    uint64_t *blob_full = mb, *stage_full = mb + WS_NB, *stage_empty = mb + WS_NB + 2;
     unsigned char *blobs = sm + L.blob;
     const size_t stage_sz = 3 * PS + 1;
     double *stage0 = reinterpret_cast<double *>(sm + L.stage);
@@ -286,12 +291,13 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
     const int n_it = (a.n_patches - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 3; k++) mbar_init(&blob_full[k], 1);
-        for (int k = 0; k < 2; k++) {
-            mbar_init(&xs_full[k], WS_H); mbar_init(&xs_empty[k], WS_T);
-            mbar_init(&stage_full[k], WS_T); mbar_init(&stage_empty[k], WS_H);
-        }
+        for (int k = 0; k < WS_NB; k++) mbar_init(&blob_full[k], 1);
+        for (int k = 0; k < 2; k++) { mbar_init(&stage_full[k], WS_T); mbar_init(&stage_empty[k], WS_H); }
         mbar_fence_init();
+        for (int k = 0; k < WS_NB && k < n_it; k++) {
+            mbar_expect_tx(&blob_full[k], a.stride);
+            bulk_g2s(blobs + (size_t)k * a.stride, a.blob + (size_t)(blockIdx.x + k * gridDim.x) * a.stride, a.stride, &blob_full[k]);
+        }
     }
     __syncthreads();
 
@@ -299,14 +305,69 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         // =========================== compute warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_COMPUTE_REGS));
         const int tid = threadIdx.x;
+        // look-ahead gather registers: flat items i = 3*node + component, thread t holds items t + r*T (consecutive
+        // lanes -> consecutive addresses wherever consecutive patch nodes have consecutive ids)
+        double rx[WS_GX], rc[WS_GC];
+        JF_UNROLL for (int r = 0; r < WS_GX; r++) rx[r] = 0.0;
+        JF_UNROLL for (int r = 0; r < WS_GC; r++) rc[r] = 0.0;
+        auto load_regs = [&](const unsigned char *bl) {
+            const int *hdr = reinterpret_cast<const int *>(bl);
+            const int n3 = 3 * hdr[0], nx3 = 3 * (int)((unsigned)hdr[1] >> 16);
+            const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+            const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
+            JF_UNROLL for (int r = 0; r < WS_GX; r++) {
+                const int i = tid + r * T, ic = i < n3 ? i : 0, j = ic / 3;
+                rx[r] = __ldg(a.x + 3 * (long long)(pn[j] & PN_ID_MASK) + (ic - 3 * j));
+            }
+            JF_UNROLL for (int r = 0; r < WS_GC; r++) {
+                const int i = tid + r * T, ic = i < nx3 ? i : 0, j = ic / 3;
+                rc[r] = __ldg(a.coords + 3 * (long long)(nx3 > 0 ? xl[j] : 0) + (ic - 3 * j));
+            }
+        };
+        // registers -> shared tiles (+ slow paths for patches with more than WS_GX*T/3 nodes)
+        auto store_regs = [&](const unsigned char *bl, double *xs, double *Xs) {
+            const int *hdr = reinterpret_cast<const int *>(bl);
+            const int n3 = 3 * hdr[0], nx3 = 3 * (int)((unsigned)hdr[1] >> 16);
+            JF_UNROLL for (int r = 0; r < WS_GX; r++) {
+                const int i = tid + r * T;
+                if (i < n3) xs[i] = rx[r];
+            }
+            JF_UNROLL for (int r = 0; r < WS_GC; r++) {
+                const int i = tid + r * T;
+                if (i < nx3) Xs[i] = rc[r];
+            }
+            const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+            const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
+            for (int i = tid + WS_GX * T; i < n3; i += T) {
+                const int j = i / 3;
+                xs[i] = __ldg(a.x + 3 * (long long)(pn[j] & PN_ID_MASK) + (i - 3 * j));
+            }
+            for (int i = tid + WS_GC * T; i < nx3; i += T) {
+                const int j = i / 3;
+                Xs[i] = __ldg(a.coords + 3 * (long long)xl[j] + (i - 3 * j));
+            }
+        };
+        if (n_it > 0) {
+            mbar_wait(&blob_full[0], 0);
+            load_regs(blobs);
+            store_regs(blobs, xs0, Xs0);
+            named_sync(2, WS_T);
+        }
         for (int i = 0; i < n_it; i++) {
-            const int p = blockIdx.x + i * gridDim.x;
-            const unsigned char *bl = blobs + (size_t)(i % 3) * a.stride;
+            const unsigned char *bl = blobs + (size_t)(i % WS_NB) * a.stride;
+            const unsigned char *bln = blobs + (size_t)((i + 1) % WS_NB) * a.stride;
             double *stage = stage0 + (size_t)(i & 1) * stage_sz;
             const double *xs = xs0 + (size_t)(i & 1) * xs_sz, *Xs = Xs0 + (size_t)(i & 1) * Xs_sz;
-            mbar_wait(&blob_full[i % 3], (i / 3) & 1);
-            mbar_wait(&xs_full[i & 1], (i >> 1) & 1);
+            const bool has_next = i + 1 < n_it;
+            const bool tm = a.timing && blockIdx.x == 0 && tid == 0 && i < 8;
+            if (tm) a.timing[i * 8 + 0] = clock64();
+            if (has_next) {
+                mbar_wait(&blob_full[(i + 1) % WS_NB], ((i + 1) / WS_NB) & 1);
+                load_regs(bln);
+            }
+            if (tm) a.timing[i * 8 + 1] = clock64();
             if (i >= 2) mbar_wait(&stage_empty[i & 1], ((i >> 1) - 1) & 1);
+            if (tm) a.timing[i * 8 + 2] = clock64();
             const int ne = reinterpret_cast<const int *>(bl)[3];
             if (tid < ne) {
                 const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
@@ -324,87 +385,69 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 SField X{Xs, nxs};
                 tet10_affine_linear(pt.la, pt.mu, U, X, out);
             }
-            (void)p;
-            mbar_arrive(&xs_empty[i & 1]);
+            if (tm) a.timing[i * 8 + 3] = clock64();
             mbar_arrive(&stage_full[i & 1]);
+            if (has_next) {
+                store_regs(bln, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
+                named_sync(2, WS_T);   // tile (i+1)&1 complete and visible to every compute warp
+            }
+            if (tm) a.timing[i * 8 + 4] = clock64();
         }
     } else {
         // =========================== helper warps ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_HELPER_REGS));
         const int hid = threadIdx.x - WS_T;
-        if (hid == 0)
-            for (int k = 0; k < 3 && k < n_it; k++) {
-                mbar_expect_tx(&blob_full[k], a.stride);
-                bulk_g2s(blobs + (size_t)k * a.stride, a.blob + (size_t)(blockIdx.x + k * gridDim.x) * a.stride, a.stride, &blob_full[k]);
-            }
-        for (int i = 0; i <= n_it; i++) {
-            if (i < n_it) {   // ---- gather patch i into x tile (i & 1)
-                const unsigned char *bl = blobs + (size_t)(i % 3) * a.stride;
-                mbar_wait(&blob_full[i % 3], (i / 3) & 1);
-                if (i >= 2) mbar_wait(&xs_empty[i & 1], ((i >> 1) - 1) & 1);
-                double *xs = xs0 + (size_t)(i & 1) * xs_sz, *Xs = Xs0 + (size_t)(i & 1) * Xs_sz;
-                const int *hdr = reinterpret_cast<const int *>(bl);
-                const int np = hdr[0], nx = (int)((unsigned)hdr[1] >> 16);
-                const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
-                const uint32_t *xl = reinterpret_cast<const uint32_t *>(bl + a.off_xl);
-                for (int j = hid; j < np; j += WS_H) {
-                    const long long g = 3 * (long long)(pn[j] & PN_ID_MASK);
-                    cp_async8(xs + 3 * j, a.x + g); cp_async8(xs + 3 * j + 1, a.x + g + 1); cp_async8(xs + 3 * j + 2, a.x + g + 2);
+        for (int k = 0; k < n_it; k++) {
+            const unsigned char *bl = blobs + (size_t)(k % WS_NB) * a.stride;
+            const double *stage = stage0 + (size_t)(k & 1) * stage_sz;
+            const bool tm = a.timing && blockIdx.x == 0 && hid == 0 && k < 8;
+            if (tm) a.timing[64 + k * 8 + 0] = clock64();
+            mbar_wait(&blob_full[k % WS_NB], (k / WS_NB) & 1);
+            mbar_wait(&stage_full[k & 1], (k >> 1) & 1);
+            if (tm) a.timing[64 + k * 8 + 1] = clock64();
+            const int *hdr = reinterpret_cast<const int *>(bl);
+            const int np = hdr[0], nif = hdr[1] & 0xFFFF, ipb = hdr[2];
+            const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
+            const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
+            for (int j = hid; j < np; j += WS_H) {
+                const int q0 = go[j], cnt = go[j + 1] - q0;
+                const double *sp = stage + q0;
+                double s0 = 0, s1 = 0, s2 = 0;
+                int q = 0;
+                for (; q + 2 <= cnt; q += 2) {
+                    const double a0 = sp[q], a1 = sp[q + 1], b0 = sp[PS + q], b1 = sp[PS + q + 1], c0 = sp[2 * PS + q], c1 = sp[2 * PS + q + 1];
+                    s0 += a0; s1 += b0; s2 += c0;
+                    s0 += a1; s1 += b1; s2 += c1;
                 }
-                for (int j = hid; j < nx; j += WS_H) {
-                    const long long g = 3 * (long long)xl[j];
-                    cp_async8(Xs + 3 * j, a.coords + g); cp_async8(Xs + 3 * j + 1, a.coords + g + 1); cp_async8(Xs + 3 * j + 2, a.coords + g + 2);
+                if (q < cnt) { s0 += sp[q]; s1 += sp[PS + q]; s2 += sp[2 * PS + q]; }
+                const uint32_t w = pn[j];
+                if (a.project) {
+                    if (w & (1u << PN_FIXSHIFT)) s0 = 0.0;
+                    if (w & (2u << PN_FIXSHIFT)) s1 = 0.0;
+                    if (w & (4u << PN_FIXSHIFT)) s2 = 0.0;
                 }
-                cp_async_mbar_arrive_noinc(&xs_full[i & 1]);   // arrives when this thread's copies have landed
-            }
-            if (i >= 1) {     // ---- reduce + store patch i-1
-                const int k = i - 1;
-                const unsigned char *bl = blobs + (size_t)(k % 3) * a.stride;
-                const double *stage = stage0 + (size_t)(k & 1) * stage_sz;
-                mbar_wait(&stage_full[k & 1], (k >> 1) & 1);
-                const int *hdr = reinterpret_cast<const int *>(bl);
-                const int np = hdr[0], nif = hdr[1] & 0xFFFF, ipb = hdr[2];
-                const uint32_t *pn = reinterpret_cast<const uint32_t *>(bl + a.off_pn);
-                const uint16_t *go = reinterpret_cast<const uint16_t *>(bl + a.off_go);
-                for (int j = hid; j < np; j += WS_H) {
-                    const int q0 = go[j], cnt = go[j + 1] - q0;
-                    const double *sp = stage + q0;
-                    double s0 = 0, s1 = 0, s2 = 0;
-                    int q = 0;
-                    for (; q + 2 <= cnt; q += 2) {
-                        const double a0 = sp[q], a1 = sp[q + 1], b0 = sp[PS + q], b1 = sp[PS + q + 1], c0 = sp[2 * PS + q], c1 = sp[2 * PS + q + 1];
-                        s0 += a0; s1 += b0; s2 += c0;
-                        s0 += a1; s1 += b1; s2 += c1;
-                    }
-                    if (q < cnt) { s0 += sp[q]; s1 += sp[PS + q]; s2 += sp[2 * PS + q]; }
-                    const uint32_t w = pn[j];
-                    if (a.project) {
-                        if (w & (1u << PN_FIXSHIFT)) s0 = 0.0;
-                        if (w & (2u << PN_FIXSHIFT)) s1 = 0.0;
-                        if (w & (4u << PN_FIXSHIFT)) s2 = 0.0;
-                    }
-                    if (j < nif) {
-                        if (a.atomic_iface) {
-                            double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
-                            atomicAdd(py, s0); atomicAdd(py + 1, s1); atomicAdd(py + 2, s2);
-                        } else {
-                            double *pp = a.ipart + 3 * ((long long)ipb + j);
-                            pp[0] = s0; pp[1] = s1; pp[2] = s2;
-                        }
-                    } else {
+                if (j < nif) {
+                    if (a.atomic_iface) {
                         double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
-                        py[0] = s0; py[1] = s1; py[2] = s2;
+                        atomicAdd(py, s0); atomicAdd(py + 1, s1); atomicAdd(py + 2, s2);
+                    } else {
+                        double *pp = a.ipart + 3 * ((long long)ipb + j);
+                        pp[0] = s0; pp[1] = s1; pp[2] = s2;
                     }
+                } else {
+                    double *py = a.y + 3 * (long long)(w & PN_ID_MASK);
+                    py[0] = s0; py[1] = s1; py[2] = s2;
                 }
-                mbar_arrive(&stage_empty[k & 1]);
-                // blob buffer (k % 3) is free once every helper thread is past the reduction: refill it with patch k+3
-                if (k + 3 < n_it) {
-                    named_sync(1, WS_H);
-                    if (hid == 0) {
-                        mbar_expect_tx(&blob_full[k % 3], a.stride);
-                        bulk_g2s(blobs + (size_t)(k % 3) * a.stride, a.blob + (size_t)(blockIdx.x + (k + 3) * gridDim.x) * a.stride, a.stride,
-                                 &blob_full[k % 3]);
-                    }
+            }
+            if (tm) a.timing[64 + k * 8 + 2] = clock64();
+            mbar_arrive(&stage_empty[k & 1]);
+            // blob slot (k % WS_NB) is free once every helper thread is past the reduction: refill it with patch k + WS_NB
+            if (k + WS_NB < n_it) {
+                named_sync(1, WS_H);
+                if (hid == 0) {
+                    mbar_expect_tx(&blob_full[k % WS_NB], a.stride);
+                    bulk_g2s(blobs + (size_t)(k % WS_NB) * a.stride, a.blob + (size_t)(blockIdx.x + (k + WS_NB) * gridDim.x) * a.stride, a.stride,
+                             &blob_full[k % WS_NB]);
                 }
             }
         }
@@ -533,7 +576,7 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
             auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
             WsSmem L;
             L.blob = 128;
-            L.stage = (int)r128(L.blob + 3 * (size_t)D.stride);
+            L.stage = (int)r128(L.blob + WS_NB * (size_t)D.stride);
             L.xs = (int)r128(L.stage + 2 * sizeof(double) * (3 * PS + 1));
             L.Xs = (int)r128(L.xs + 2 * sizeof(double) * 3 * D.max_nodes);
             L.total = (int)r128(L.Xs + 2 * sizeof(double) * 3 * D.max_nx);
