@@ -87,7 +87,7 @@ int jfem_destroy(jfem_handle *h);
 /* tuning knobs, before the first operator call: "patch_elems" (elements per thread-block patch),
  * "deterministic" (1: ordered interface reduction [default], 0: fp64 atomics), "affine_fast_path" (1/0) */
 int jfem_set_option(jfem_handle *h, const char *key, double value);
-/* homogeneous material (per_element == 0: params has n_params entries) or per-element
+/* homogeneous material (per_element == 0: params has n_params entries, 2 <= n_params <= 4) or per-element
  * (per_element != 0: params is n_params x n_elems column-major), like E_vec/nu_vec of ext:135-141 */
 int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_params, int per_element);
 /* is_fixed / prescribed of ext:144-158.  dofs use index_base given at creation. */

@@ -156,8 +156,13 @@ class Handle:
         check(lib().jfem_set_option(self._h, key.encode(), float(value)))
 
     def set_material(self, kind, params):
+        """params: (n_params,) homogeneous, or (n_elems, n_params) per element (row e = parameters of element e)."""
         p = np.ascontiguousarray(params, dtype=np.float64)
-        check(lib().jfem_set_material(self._h, kind, p.ctypes.data_as(C.c_void_p), p.size, 0))
+        if p.ndim == 2:
+            assert p.shape[0] == self.n_elems
+            check(lib().jfem_set_material(self._h, kind, p.ctypes.data_as(C.c_void_p), p.shape[1], 1))
+        else:
+            check(lib().jfem_set_material(self._h, kind, p.ctypes.data_as(C.c_void_p), p.size, 0))
 
     def set_dirichlet(self, dofs, values=None):
         d = np.ascontiguousarray(dofs, dtype=np.int64)

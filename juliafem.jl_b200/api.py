@@ -193,11 +193,10 @@ def _material_of(elements, properties, explicit=None):
     nu = {_get(el, "poissons ratio", "poissons_ratio") for el in elements}
     if None in E or None in nu:
         raise KeyError("elements need \"youngs modulus\" and \"poissons ratio\" fields")   # reference: KeyError from element(...)
-    if len(E) != 1 or len(nu) != 1:
-        raise NotImplementedError("per-element material parameters are not supported yet (homogeneous only)")
-    if getattr(properties, "finite_strain", False):
-        return _lib.MAT_NEO_HOOKEAN, (E.pop(), nu.pop())
-    return _lib.MAT_LINEAR_ELASTIC, (E.pop(), nu.pop())
+    kind = _lib.MAT_NEO_HOOKEAN if getattr(properties, "finite_strain", False) else _lib.MAT_LINEAR_ELASTIC
+    if len(E) != 1 or len(nu) != 1:      # per-element arrays, like E_vec / nu_vec of ext/JuliaFEMCUDAExt.jl:135-141
+        return kind, np.array([[_get(el, "youngs modulus", "youngs_modulus"), _get(el, "poissons ratio", "poissons_ratio")] for el in elements])
+    return kind, (E.pop(), nu.pop())
 
 
 class ElasticityDataGPU:

@@ -104,7 +104,7 @@ int jfem_destroy(jfem_handle *h) {
     cudaStreamSynchronize(h->stream);
     jfem_comm_destroy(h);
     for (int c = 0; c < N_CLASSES; c++) h->dsets[c].release();
-    h->inodes.release(); h->iptr.release(); h->islots.release(); h->islot4.release(); h->ipart.release(); h->coords.release(); h->fixed.release();
+    h->matp.release(); h->inodes.release(); h->iptr.release(); h->islots.release(); h->islot4.release(); h->ipart.release(); h->coords.release(); h->fixed.release();
     h->prescribed.release(); h->ulin.release(); h->st_old.release(); h->st_new.release(); h->dflags.release(); h->wx.release(); h->wy.release();
     h->cg_r.release(); h->cg_p.release(); h->cg_Ap.release(); h->cg_z.release(); h->cg_dinv.release(); h->nk_R.release(); h->nk_du.release();
     h->nk_f.release(); h->red_partials.release(); h->cg_s.release(); h->nadj_ptr.release(); h->rowptr.release(); h->nadj.release();
@@ -141,16 +141,21 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
 
 int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_params, int per_element) {
     CHECK_H(h);
-    if (per_element) { jfem_set_error("per-element material parameters are not supported yet (homogeneous only)"); return JFEM_EINVAL; }
     const int need = kind == JFEM_MAT_PERFECT_PLASTICITY ? 4 : 2;
-    if (kind < 0 || kind > 2 || !params || n_params < need) { jfem_set_error("jfem_set_material: bad kind/params"); return JFEM_EINVAL; }
-    const double E = params[0], nu = params[1];
-    // parameter validation of the reference constructors (linear_elastic.jl:51-56, perfect_plasticity.jl:176-181)
-    if (!(E > 0.0)) { jfem_set_error("Young's modulus must be positive, got E = %g", E); return JFEM_EINVAL; }
-    if (!(nu > -1.0 && nu < 0.5)) { jfem_set_error("Poisson's ratio must be in (-1, 0.5), got nu = %g", nu); return JFEM_EINVAL; }
-    if (kind == JFEM_MAT_PERFECT_PLASTICITY && !(params[2] > 0.0 && params[3] >= 0.0)) {
-        jfem_set_error("yield stress must be positive and hardening modulus non-negative"); return JFEM_EINVAL;
+    if (kind < 0 || kind > 2 || !params || n_params < need || n_params > 4) { jfem_set_error("jfem_set_material: bad kind/params"); return JFEM_EINVAL; }
+    const int64_t nsets = per_element ? h->mesh.n_elems : 1;
+    for (int64_t e = 0; e < nsets; e++) {
+        const double *q = params + e * n_params;
+        const double E = q[0], nu = q[1];
+        // parameter validation of the reference constructors (linear_elastic.jl:51-56, perfect_plasticity.jl:176-181)
+        if (!(E > 0.0)) { jfem_set_error("Young's modulus must be positive, got E = %g", E); return JFEM_EINVAL; }
+        if (!(nu > -1.0 && nu < 0.5)) { jfem_set_error("Poisson's ratio must be in (-1, 0.5), got nu = %g", nu); return JFEM_EINVAL; }
+        if (kind == JFEM_MAT_PERFECT_PLASTICITY && !(q[2] > 0.0 && q[3] >= 0.0)) {
+            jfem_set_error("yield stress must be positive and hardening modulus non-negative"); return JFEM_EINVAL;
+        }
     }
+    if (per_element) { h->mat_per_elem.assign(params, params + (size_t)n_params * h->mesh.n_elems); h->mat_nparams = n_params; }
+    else { h->mat_per_elem.clear(); h->mat_nparams = 0; h->matp.release(); }
     const bool want_affine_prev = h->affine && h->mat_kind == JFEM_MAT_LINEAR_ELASTIC;
     h->mat_kind = kind;
     for (int i = 0; i < 4; i++) h->mat[i] = i < n_params ? params[i] : 0.0;
@@ -158,6 +163,7 @@ int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_para
     if (kind != JFEM_MAT_LINEAR_ELASTIC && h->affine) { h->affine = false; h->built = false; }
     (void)want_affine_prev;
     if (kind == JFEM_MAT_PERFECT_PLASTICITY && h->built && h->st_old.n == 0) h->built = false;
+    if (h->built) return upload_material(h);
     return JFEM_OK;
 }
 

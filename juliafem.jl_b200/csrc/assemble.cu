@@ -15,6 +15,8 @@
 
 using namespace jf;
 
+void fill_material(const jfem_handle *h, jf::MatBase &m);
+
 // global-memory field accessor; base == nullptr means "unit vector e_(kj,cj)"
 struct AField {
     const double *base;
@@ -262,13 +264,11 @@ static int launch_columns(jfem_handle *h, AsmArgs a, const Pt &pt) {
 
 template <int NNPE>
 static int columns_by_material(jfem_handle *h, AsmArgs a) {
-    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
-    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
-    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; pt.la = la; pt.mu = mu; return launch_columns<NNPE>(h, a, pt); }
-    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; pt.la = la; pt.mu = mu; return launch_columns<NNPE>(h, a, pt); }
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; fill_material(h, pt); return launch_columns<NNPE>(h, a, pt); }
+    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; fill_material(h, pt); return launch_columns<NNPE>(h, a, pt); }
     if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY) {
-        PtPPTangent pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.n_gp = n_gp;
+        PtPPTangent pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.n_gp = n_gp;
         return launch_columns<NNPE>(h, a, pt);
     }
     jfem_set_error("material not set");
@@ -330,14 +330,12 @@ int csr_spmv(jfem_handle *h, const double *x, double *y, int flags, const int *d
 
 template <int NNPE>
 static int fint_by_material(jfem_handle *h, AsmArgs a, double *fe) {
-    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
-    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
     const unsigned blocks = (unsigned)((a.ne + 127) / 128);
-    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; pt.la = la; pt.mu = mu; elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
-    else if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHResidual pt; pt.la = la; pt.mu = mu; elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; fill_material(h, pt); elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
+    else if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHResidual pt; fill_material(h, pt); elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
     else {
-        PtPPResidual pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.st_new = nullptr; pt.n_gp = n_gp;
+        PtPPResidual pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.st_new = nullptr; pt.n_gp = n_gp;
         elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe);
     }
     JFEM_CUDA(cudaGetLastError());
@@ -417,12 +415,10 @@ static int launch_diag(jfem_handle *h, AsmArgs a, const Pt &pt, double *D) {
 
 template <int NNPE>
 static int diag_by_material(jfem_handle *h, AsmArgs a, double *D, bool tangent) {
-    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));
-    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
-    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || !tangent) { PtLinear pt; pt.la = la; pt.mu = mu; return launch_diag<NNPE>(h, a, pt, D); }
-    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; pt.la = la; pt.mu = mu; return launch_diag<NNPE>(h, a, pt, D); }
-    PtPPTangent pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3]; pt.st_old = h->st_old.p; pt.n_gp = n_gp;
+    if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || !tangent) { PtLinear pt; fill_material(h, pt); return launch_diag<NNPE>(h, a, pt, D); }
+    if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; fill_material(h, pt); return launch_diag<NNPE>(h, a, pt, D); }
+    PtPPTangent pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.n_gp = n_gp;
     return launch_diag<NNPE>(h, a, pt, D);
 }
 

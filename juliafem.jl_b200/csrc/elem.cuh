@@ -53,10 +53,25 @@ struct SField {
 // Point functors: P[i][j] from displacement gradients.  G[f][i][j] = d(field f)_i / dx_j.
 // ------------------------------------------------------------------------------------------------
 
+// Material parameters: homogeneous (pe == nullptr) or per element (pe = SoA [param][internal element], like the
+// E_vec / nu_vec arrays of ext/JuliaFEMCUDAExt.jl:135-141).  load() is called once per element.
+struct MatBase {
+    double la, mu, sy, H;
+    const double *pe;
+    long long pe_n;
+    __device__ __forceinline__ void load(long long elem) {
+        if (pe) {
+            const double E = pe[elem], nu = pe[pe_n + elem];
+            la = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));   // src/materials/linear_elastic.jl:82
+            mu = E / (2.0 * (1.0 + nu));                     // :97
+            sy = pe[2 * pe_n + elem]; H = pe[3 * pe_n + elem];
+        }
+    }
+};
+
 // sigma = la tr(eps) I + 2 mu eps  (src/materials/linear_elastic.jl:136-158; problems_elasticity.jl:313-332)
-struct PtLinear {
+struct PtLinear : MatBase {
     static constexpr int NF = 1;
-    double la, mu;
     __device__ __forceinline__ bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
         double tr = la * (G[0][0][0] + G[0][1][1] + G[0][2][2]);
         double s01 = mu * (G[0][0][1] + G[0][1][0]), s12 = mu * (G[0][1][2] + G[0][2][1]), s02 = mu * (G[0][0][2] + G[0][2][0]);
@@ -75,8 +90,7 @@ __device__ __forceinline__ void sym6_to_33(const double (&s)[6], double (&S)[3][
 // S = 2 dpsi/dC = mu (I - C^-1) + la lnJ C^-1 ;  DD = 4 d2psi/dC2 = la Ci(x)Ci + 2(mu - la lnJ) I_{Ci}
 // (closed form of the Tensors.hessian call at neo_hookean.jl:222).  Total Lagrangian: P = F S,
 // dP = dF S + F (DD : sym(F' dF))  -- material + geometric stiffness (problems_elasticity.jl:270-289,378-404).
-struct NHCommon {
-    double la, mu;
+struct NHCommon : MatBase {
     __device__ __forceinline__ bool kin(const double (&Gu)[3][3], double (&F)[3][3], double (&Ci)[3][3], double &lnJ) const {
         JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) F[i][j] = Gu[i][j] + (i == j ? 1.0 : 0.0);
         double C[3][3];
@@ -126,8 +140,7 @@ struct PtNHTangent : NHCommon {   // field 0 = v (direction), field 1 = u (linea
 
 // J2 plasticity with linear kinematic hardening, radial return (src/materials/perfect_plasticity.jl:247-341).
 // State per Gauss point, SoA: st[s * n_gp + gp], s = 0..12 (eps_p 11,22,33,12,23,13 ; alpha ; kappa).
-struct PPCommon {
-    double la, mu, sy, H;
+struct PPCommon : MatBase {
     const double *st_old;
     long long n_gp;
     // returns true if plastic; s = stress (tensor comps), n = flow direction s_trial/q, dl = plastic multiplier
@@ -202,8 +215,10 @@ struct PtPPTangent : PPCommon {   // field 0 = v, field 1 = u;  dP = DD_ep : sym
 // X the coordinates; out(k, v0, v1, v2) receives the 3 components of node k of the element vector.  Returns false on invalid deformation.
 // ------------------------------------------------------------------------------------------------
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool tet10_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+__device__ __forceinline__ bool tet10_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
+    Pt pt = pt0;
+    pt.load(elem);
     const double c1 = 4.0 * T10_B - 1.0, c4b = 4.0 * T10_B, k4 = 4.0 * (T10_A - T10_B);
     double bx[4][3], bu[NF][4][3];
     JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int c = 0; c < 3; c++) {
@@ -323,8 +338,10 @@ __device__ __forceinline__ void tet10_affine_linear(double la, double mu, const 
 // Tet4, GLTET1 (src/quadrature/gltet.jl:7-11): constant gradient.
 // ------------------------------------------------------------------------------------------------
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool tet4_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+__device__ __forceinline__ bool tet4_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
+    Pt pt = pt0;
+    pt.load(elem);
     double J[3][3], iJ[3][3];
     JF_UNROLL for (int a = 0; a < 3; a++) JF_UNROLL for (int c = 0; c < 3; c++) J[a][c] = X(a + 1, c) - X(0, c);
     double det = inv3x3(J, iJ);
@@ -369,8 +386,10 @@ __device__ __forceinline__ void hex8_modal(const double (&q)[8], double (&m)[8])
 #define HEX_GA 0.5773502691896258
 
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool hex8_general(const Pt &pt, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+__device__ __forceinline__ bool hex8_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
+    Pt pt = pt0;
+    pt.load(elem);
     double mx[3][8], mu_[NF][3][8];
     JF_UNROLL for (int c = 0; c < 3; c++) {
         double q[8];

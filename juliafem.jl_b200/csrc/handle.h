@@ -23,7 +23,9 @@ struct jfem_handle {
     // material
     int mat_kind = -1;
     double mat[4] = {0, 0, 0, 0};
-    std::vector<double> mat_per_elem;   // unused when homogeneous
+    std::vector<double> mat_per_elem;   // n_params x n_elems (caller order), empty when homogeneous
+    int mat_nparams = 0;
+    DevBuf<double> matp;                // 4 x n_elems SoA in internal element order
     // patches
     bool built = false;
     double setup_seconds = 0;
@@ -97,6 +99,7 @@ int op_apply(jfem_handle *h, int mode, const double *x_dev, double *y_dev, int f
 int halo_exchange(jfem_handle *h, double *x_dev);
 int comm_allreduce_sum(jfem_handle *h, double *buf_dev, int count);
 int upload_fixed(jfem_handle *h);
+int upload_material(jfem_handle *h);
 
 int cg_solve(jfem_handle *h, const double *b_dev, double *x_dev, double tol, int rel, int max_iter, int flags, int *iters, double *resid);
 int newton_krylov(jfem_handle *h, const double *fext_dev, double *u_dev, double newton_tol, int max_newton, int max_cg,

@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(T * G, 1) patch_kernel(PatchKArgs a, Pt pt) {
                 JF_UNROLL for (int k = 0; k < 4; k++) nxs[k] = xsl[n[k]];
                 SField U{xs, n};
                 SField X{Xs, nxs};
-                tet10_affine_linear(pt.la, pt.mu, U, X, out);
+                PtLinear q; q.la = pt.la; q.mu = pt.mu; q.sy = 0; q.H = 0; q.pe = pt.pe; q.pe_n = pt.pe_n;
+                q.load(el);
+                tet10_affine_linear(q.la, q.mu, U, X, out);
             } else {
                 int nxs[NNPE];
                 JF_UNROLL for (int k = 0; k < NNPE; k++) nxs[k] = xsl[n[k]];
@@ -383,7 +385,9 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 };
                 SField U{xs, n};
                 SField X{Xs, nxs};
-                tet10_affine_linear(pt.la, pt.mu, U, X, out);
+                Pt q = pt;
+                q.load(a.elem_offset + (long long)(blockIdx.x + i * gridDim.x) * T + tid);
+                tet10_affine_linear(q.la, q.mu, U, X, out);
             }
             if (tm) a.timing[i * 8 + 3] = clock64();
             mbar_arrive(&stage_full[i & 1]);
@@ -519,6 +523,21 @@ int upload_fixed(jfem_handle *h) {   // (re)upload everything that embeds the Di
     return JFEM_OK;
 }
 
+// per-element parameters: caller order (n_params x n_elems) -> SoA [4][n_elems] in internal element order
+int upload_material(jfem_handle *h) {
+    if (h->mat_per_elem.empty()) { h->matp.release(); return JFEM_OK; }
+    const int64_t ne = h->mesh.n_elems;
+    std::vector<double> soa(4 * (size_t)ne, 0.0);
+    int64_t off = 0;
+    for (int c = 0; c < N_CLASSES; c++) {
+        const PatchSetHost &S = h->hsets[c];
+        for (int64_t i = 0; i < S.n_elems; i++)
+            for (int q = 0; q < h->mat_nparams; q++) soa[(size_t)q * ne + off + i] = h->mat_per_elem[(size_t)S.elem_perm[i] * h->mat_nparams + q];
+        off += S.n_elems;
+    }
+    return h->matp.upload(soa);
+}
+
 int ensure_built(jfem_handle *h) {
     if (h->built) return JFEM_OK;
     JFEM_CUDA(cudaSetDevice(h->device));
@@ -555,6 +574,7 @@ int ensure_built(jfem_handle *h) {
     JFEM_CUDA(cudaMemset(h->dflags.p, 0, 4 * sizeof(int)));
     h->built = true;
     JFEM_TRY(upload_fixed(h));
+    JFEM_TRY(upload_material(h));
     if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY && h->st_old.n == 0) {
         size_t n = (size_t)JFEM_NSTATE * h->ngp() * h->mesh.n_elems;
         JFEM_TRY(h->st_old.alloc(n));
@@ -621,28 +641,34 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
     return JFEM_OK;
 }
 
+void fill_material(const jfem_handle *h, jf::MatBase &m) {
+    m.la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));   // linear_elastic.jl:82
+    m.mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));                                    // :97
+    m.sy = h->mat[2]; m.H = h->mat[3];
+    m.pe = h->matp.n ? h->matp.p : nullptr;
+    m.pe_n = h->mesh.n_elems;
+}
+
 template <int NNPE, int CLS, int T>
 static int dispatch_mode(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, int mode) {
-    double la = h->mat[0] * h->mat[1] / ((1.0 + h->mat[1]) * (1.0 - 2.0 * h->mat[1]));   // linear_elastic.jl:82
-    double mu = h->mat[0] / (2.0 * (1.0 + h->mat[1]));                                    // :97
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
     if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || (mode == OP_LINEAR)) {
         // small-strain linear elasticity: K.x = f_int(x), tangent == K
-        PtLinear pt; pt.la = la; pt.mu = mu;
+        PtLinear pt; fill_material(h, pt);
         return launch_set<NNPE, CLS, OP_LINEAR, PtLinear, T>(h, D, a, pt);
     }
     if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) {
-        if (mode == OP_RESIDUAL) { PtNHResidual pt; pt.la = la; pt.mu = mu; return launch_set<NNPE, CLASS_GENERAL, OP_RESIDUAL, PtNHResidual, T>(h, D, a, pt); }
-        PtNHTangent pt; pt.la = la; pt.mu = mu;
+        if (mode == OP_RESIDUAL) { PtNHResidual pt; fill_material(h, pt); return launch_set<NNPE, CLASS_GENERAL, OP_RESIDUAL, PtNHResidual, T>(h, D, a, pt); }
+        PtNHTangent pt; fill_material(h, pt);
         return launch_set<NNPE, CLASS_GENERAL, OP_TANGENT, PtNHTangent, T>(h, D, a, pt);
     }
     if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY) {
         if (mode == OP_RESIDUAL) {
-            PtPPResidual pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3];
+            PtPPResidual pt; fill_material(h, pt);
             pt.st_old = h->st_old.p; pt.st_new = h->st_new.p; pt.n_gp = n_gp;
             return launch_set<NNPE, CLASS_GENERAL, OP_RESIDUAL, PtPPResidual, T>(h, D, a, pt);
         }
-        PtPPTangent pt; pt.la = la; pt.mu = mu; pt.sy = h->mat[2]; pt.H = h->mat[3];
+        PtPPTangent pt; fill_material(h, pt);
         pt.st_old = h->st_old.p; pt.n_gp = n_gp;
         return launch_set<NNPE, CLASS_GENERAL, OP_TANGENT, PtPPTangent, T>(h, D, a, pt);
     }

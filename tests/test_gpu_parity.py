@@ -342,3 +342,29 @@ def test_block_jacobi_pcg(L, oracle, jf):
     r = b - oracle.spmv(rp, ci, vals, x1); r[fixed - 1] = 0
     bn = b.copy(); bn[fixed - 1] = 0
     assert np.linalg.norm(r) <= 5e-9 * np.linalg.norm(bn)
+
+
+def test_per_element_material(L, oracle, jf):
+    """Per-element E, nu (E_vec / nu_vec of ext/JuliaFEMCUDAExt.jl:135-141): affine kernel, curved kernel, assembled path."""
+    for m in (jf.mesh.tet10_kuhn(4, 2, 2), curved_tet10(jf.mesh, 3, 2, 2)):
+        rng = np.random.default_rng(3)
+        par = np.stack([210e9 * (0.5 + rng.random(m.n_elems)), 0.2 + 0.2 * rng.random(m.n_elems)], axis=1)
+        u = jf.mesh.test_vector(m.n_dofs)
+        ref = np.zeros(m.n_dofs)
+        for e in range(m.n_elems):
+            Ke, _, _, _ = oracle.element(10, m.coords[m.conn[e] - 1], par=tuple(par[e]))
+            g = (3 * (m.conn[e][:, None] - 1) + np.arange(3)[None, :]).ravel()
+            ref[g] += Ke @ u[g]
+        h = L.Handle(10, m.coords, m.conn)
+        h.set_material(0, par)
+        assert relerr(h.matvec(u), ref) < TOL
+        K, _ = h.element_matrices()
+        Ke, _, _, _ = oracle.element(10, m.coords[m.conn[5] - 1], par=tuple(par[5]))
+        assert relerr(K[5], Ke) < TOL
+        h.assemble_csr()
+        assert relerr(h.spmv(u), ref) < TOL
+        # switching back to a homogeneous material works
+        h.set_material(0, LE)
+        assert relerr(h.matvec(u), oracle.matfree(10, m.coords, m.conn, u, par=LE)) < TOL
+    with pytest.raises(L.JfemError):
+        h.set_material(0, np.array([[1.0, 0.3]] * (m.n_elems - 1) + [[-1.0, 0.3]]))
