@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
             if (tm) a.timing[i * 8 + 0] = clock64();
             if (has_next) {
                 mbar_wait(&blob_full[(i + 1) % WS_NB], ((i + 1) / WS_NB) & 1);
+                if (tm) a.timing[i * 8 + 5] = clock64();
                 load_regs(bln);
             }
             if (tm) a.timing[i * 8 + 1] = clock64();

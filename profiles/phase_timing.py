@@ -19,7 +19,7 @@ for k in range(3):
     base = c[0, 0]
     for it in range(7):
         r = c[it]
-        print(f"compute it {it} start {r[0]-base:6d} blobwait+ldg {r[1]-r[0]:5d} stage_empty-wait {r[2]-r[1]:5d} ph1 {r[3]-r[2]:5d} store+sync {r[4]-r[3]:5d}")
+        print(f"compute it {it} start {r[0]-base:6d} blobwait {max(r[5]-r[0],0):5d} ldg-issue {r[1]-max(r[5],r[0]):5d} stage_empty-wait {r[2]-r[1]:5d} ph1 {r[3]-r[2]:5d} store+sync {r[4]-r[3]:5d}")
     for it in range(7):
         r = hp[it]
         print(f"helper  it {it} start {r[0]-base:6d} wait {r[1]-r[0]:5d} ph2 {r[2]-r[1]:5d}")
