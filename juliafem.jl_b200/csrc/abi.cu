@@ -104,7 +104,7 @@ int jfem_destroy(jfem_handle *h) {
     cudaStreamSynchronize(h->stream);
     jfem_comm_destroy(h);
     for (int c = 0; c < N_CLASSES; c++) h->dsets[c].release();
-    h->matp.release(); h->inodes.release(); h->iptr.release(); h->islots.release(); h->islot4.release(); h->ipart.release(); h->coords.release(); h->fixed.release();
+    h->matp.release(); h->inodes.release(); h->ibase.release(); h->ipart.release(); h->gbar.release(); h->slot_node.release(); h->coords.release(); h->fixed.release();
     h->prescribed.release(); h->ulin.release(); h->st_old.release(); h->st_new.release(); h->dflags.release(); h->wx.release(); h->wy.release();
     h->cg_r.release(); h->cg_p.release(); h->cg_Ap.release(); h->cg_z.release(); h->cg_dinv.release(); h->nk_R.release(); h->nk_du.release();
     h->nk_f.release(); h->red_partials.release(); h->cg_s.release(); h->nadj_ptr.release(); h->rowptr.release(); h->nadj.release();
@@ -127,6 +127,14 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         else h->timing.release();
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
+    } else if (!strcmp(key, "fused_interface")) {
+        h->fused_iface = value != 0;
+    } else if (!strcmp(key, "debug_skip")) {
+        h->debug_skip = (int)value;
+    } else if (!strcmp(key, "lane_window")) {
+        int v = (int)value;
+        if (v < 0 || v > 4096) { jfem_set_error("lane_window must be in [0, 4096]"); return JFEM_EINVAL; }
+        if (v != h->lane_window) { h->lane_window = v; h->built = false; }
     } else if (!strcmp(key, "deterministic")) {
         h->deterministic = value != 0;
     } else if (!strcmp(key, "affine_fast_path")) {
@@ -198,7 +206,7 @@ int jfem_get_info(jfem_handle *h, jfem_info *info) {
         }
         info->n_affine_elems = h->dsets[CLASS_AFFINE].n_elems;
         info->n_interface_nodes = (int64_t)h->hif.inodes.size();
-        info->device_bytes += (int64_t)(h->inodes.bytes() + h->iptr.bytes() + h->islots.bytes() + h->ipart.bytes() + h->coords.bytes() + h->fixed.bytes() +
+        info->device_bytes += (int64_t)(h->inodes.bytes() + h->ibase.bytes() + h->ipart.bytes() + h->coords.bytes() + h->fixed.bytes() +
                                         h->st_old.bytes() + h->st_new.bytes() + h->ulin.bytes() + h->cg_r.bytes() * 3 + h->rowptr.bytes() + h->colind.bytes() +
                                         h->vals.bytes() + h->eblk.bytes() + h->nadj.bytes() + h->nadj_ptr.bytes() + h->dconn.bytes() + h->e2i.bytes());
     }

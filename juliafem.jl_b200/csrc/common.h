@@ -28,14 +28,15 @@ void jfem_set_error(const char *fmt, ...);
         if (rc__ != JFEM_OK) return rc__; \
     } while (0)
 
-// ---- patch node word: [31] interface  [30:28] fixed-dof mask (x,y,z)  [27] coords needed  [26:0] node id
+// ---- patch node word: [31] interface  [30:28] fixed-dof mask (x,y,z)  [26:0] node id (interior) / partial slot (interface)
 #define PN_ID_MASK 0x07FFFFFFu
-#define PN_NEEDX (1u << 27)
 #define PN_FIXSHIFT 28
 #define PN_IFACE (1u << 31)
 #define JFEM_MAX_NODES (1 << 27)
 
 enum { CLASS_GENERAL = 0, CLASS_AFFINE = 1, N_CLASSES = 2 };
+// modes of the element operator
+enum { OP_LINEAR = 0, OP_RESIDUAL = 1, OP_TANGENT = 2 };
 
 template <class T>
 struct DevBuf {
@@ -65,42 +66,61 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Per-patch metadata blob (what the kernels stream into shared memory by TMA bulk copies).  Three parts with different
+// lifetimes inside the kernel, each starting with the same 16-byte header {np, nx, ne, nrows}:
+//   part A  gather lists      pn u32[max_nodes]  node ids in GATHER order p (ascending id: coalesced loads of x)
+//                             xl u32[max_nx]     ids of the nodes whose coordinates are needed (affine Tet10: the
+//                                                element vertices; empty when every node needs them -> pn is used)
+//   part B  element table     et u32[(nnpe + nxr) * EP]   row k < nnpe, lane t:  p(node k) | staging entry << 16
+//                                                         rows nnpe.. (affine Tet10 only): coordinate slots, two u16 per word
+//   part C  reduce tables     qn u32[max_nodes]  node words in REDUCE order q (descending contribution count): interface
+//                                                flag, fixed-dof mask and the node id (interior node: the sum goes
+//                                                to y) or the partial slot of this (patch, node) (interface node)
+//                             ql u8 [max_nodes]  contribution count of the node
+//                             jo u16[max_rows+1] row offsets of the jagged staging tile
+// Staging tile (shared memory, AoS, 3 doubles per entry): row r holds the r-th contribution of every node that has more
+// than r contributions, nodes in q order -> entry(r, q) = jo[r] + q.  The reduction reads it with consecutive lanes on
+// consecutive words; the element threads scatter into it through the precomputed entry index.
+struct PatchLayout {
+    int offA = 0, off_pn = 0, off_xl = 0;
+    int offB = 0, off_et = 0;
+    int offC = 0, off_qn = 0, off_ql = 0, off_jo = 0;
+    int stride = 0;
+    int bytesA() const { return offB - offA; }
+    int bytesB() const { return offC - offB; }
+    int bytesC() const { return stride - offC; }
+};
+
 // Host-side description of one homogeneous set of patches (all elements of one class).
 struct PatchSetHost {
     int cls = CLASS_GENERAL;
-    int nnpe = 0, EP = 0;              // nodes per element, elements per patch (= threads per block)
+    int nnpe = 0, EP = 0;              // nodes per element, elements per patch (= element threads per block)
+    int nxr = 0;                       // extra element-table rows holding coordinate slots (2 for affine Tet10, else 0)
     int64_t n_elems = 0;               // elements in this set
-    int n_patches = 0, max_nodes = 0;
-    std::vector<int64_t> elem_perm;    // internal order -> caller element index (0-based)
+    int n_patches = 0, max_nodes = 0, max_nx = 0, max_rows = 0, max_entries = 0;
+    std::vector<int64_t> elem_perm;    // internal order -> caller element index (0-based); lane t of patch p = elem_perm[p*EP+t]
     std::vector<int32_t> pnode_ptr;    // n_patches+1
-    std::vector<uint32_t> pnodes;      // patch node words; interface nodes first
-    std::vector<int32_t> n_iface;      // per patch
-    std::vector<int32_t> ipart_base;   // per patch: first interface-partial slot (in nodes)
-    std::vector<uint16_t> lconn;       // [(p*nnpe+k)*EP + t] local node index (0xFFFF = no element)
-    std::vector<uint16_t> goff;        // per patch Np+1 offsets, at pnode_ptr[p]+p
-    std::vector<uint16_t> gslots;      // per patch [k*EP + t]: position of element t's node k in the node-major staging tile
-    std::vector<uint16_t> xslot;       // per patch node: slot in the compact coordinate tile (0xFFFF: coordinates not needed)
-    int max_nx = 0;                    // max #nodes per patch whose coordinates are needed
-    // everything above packed per patch into one 16-byte aligned blob (what the kernel streams in by TMA bulk copy):
-    //   [0,16) header {np, n_iface | nx<<16, ipart_base, n_elems} | pnodes u32[max_nodes] | xlist u32[max_nx] (ids of the nodes
-    //   whose coordinates are needed) | xslot u16[max_nodes] | goff u16[max_nodes+1] | rank u8[nnpe*EP] | lconn u16[nnpe*EP]
+    std::vector<uint32_t> qnodes;      // node words in reduce order (kept to re-embed the Dirichlet mask)
+    std::vector<int32_t> qids;         // node id of every entry of qnodes
+    PatchLayout L;
     std::vector<uint8_t> blob;
-    int off_pn = 0, off_xl = 0, off_xs = 0, off_go = 0, off_gs = 0, off_lc = 0, stride = 0;
+    // layout statistics (modelled shared-memory wavefronts of the element threads per patch, before / after lane assignment)
+    double wf_before = 0, wf_after = 0, wf_ideal = 0;
 };
 
 struct PatchSetDev {
-    int cls = 0, nnpe = 0, EP = 0, n_patches = 0, max_nodes = 0;
+    int cls = 0, nnpe = 0, EP = 0, nxr = 0, n_patches = 0, max_nodes = 0, max_nx = 0, max_rows = 0, max_entries = 0;
     int64_t n_elems = 0, elem_offset = 0;  // offset of this set in the internal element order
-    int max_nx = 0, off_pn = 0, off_xl = 0, off_xs = 0, off_go = 0, off_gs = 0, off_lc = 0, stride = 0;
+    PatchLayout L;
     DevBuf<uint8_t> blob;
     size_t bytes() const { return blob.bytes(); }
     void release() { blob.release(); }
 };
 
 struct InterfaceHost {
-    std::vector<uint32_t> inodes;   // node words (id + fixed mask) of interface nodes, ascending id
-    std::vector<int32_t> iptr;      // n_inodes+1
-    std::vector<int32_t> islots;    // partial slots (node units) in ascending (set, patch) order
+    std::vector<uint32_t> inodes;   // ids of interface nodes (touched by more than one patch), ascending
+    std::vector<int32_t> ibase;     // first partial slot of each interface node (its slots are contiguous, ascending (set, patch))
+    std::vector<uint32_t> orphans;  // nodes no element touches (y = 0)
     int64_t n_partials = 0;         // total interface incidences
 };
 
@@ -116,5 +136,5 @@ struct MeshHost {
     std::vector<uint8_t> cls;       // per element class
 };
 
-int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost sets[N_CLASSES], InterfaceHost &iface);
+int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, PatchSetHost sets[N_CLASSES], InterfaceHost &iface);
 void classify_elements(MeshHost &m, bool use_affine);

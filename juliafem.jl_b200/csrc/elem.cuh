@@ -14,6 +14,7 @@
 namespace jf {
 
 #define JF_UNROLL _Pragma("unroll")
+#define JF_HD __host__ __device__ __forceinline__   // host instantiation is used by the CPU-side layout check only (tests/hostcheck)
 
 // GLTET4 abscissae (5+3*sqrt(5))/20 and (5-sqrt(5))/20
 #define T10_A 0.58541019662496845
@@ -26,7 +27,7 @@ __host__ __device__ constexpr int t10_edge(int a, int b) {
                                 : 9;
 }
 
-__device__ __forceinline__ double inv3x3(const double (&J)[3][3], double (&iJ)[3][3]) {
+JF_HD double inv3x3(const double (&J)[3][3], double (&iJ)[3][3]) {
     double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
     double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
     double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
@@ -46,7 +47,7 @@ __device__ __forceinline__ double inv3x3(const double (&J)[3][3], double (&iJ)[3
 struct SField {
     const double *base;   // 3 doubles per patch node
     const int *n;         // local node index of the element's nodes
-    __device__ __forceinline__ double operator()(int k, int c) const { return base[3 * n[k] + c]; }
+    JF_HD double operator()(int k, int c) const { return base[3 * n[k] + c]; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -59,7 +60,7 @@ struct MatBase {
     double la, mu, sy, H;
     const double *pe;
     long long pe_n;
-    __device__ __forceinline__ void load(long long elem) {
+    JF_HD void load(long long elem) {
         if (pe) {
             const double E = pe[elem], nu = pe[pe_n + elem];
             la = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));   // src/materials/linear_elastic.jl:82
@@ -72,7 +73,7 @@ struct MatBase {
 // sigma = la tr(eps) I + 2 mu eps  (src/materials/linear_elastic.jl:136-158; problems_elasticity.jl:313-332)
 struct PtLinear : MatBase {
     static constexpr int NF = 1;
-    __device__ __forceinline__ bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
+    JF_HD bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
         double tr = la * (G[0][0][0] + G[0][1][1] + G[0][2][2]);
         double s01 = mu * (G[0][0][1] + G[0][1][0]), s12 = mu * (G[0][1][2] + G[0][2][1]), s02 = mu * (G[0][0][2] + G[0][2][0]);
         P[0][0] = tr + 2 * mu * G[0][0][0]; P[1][1] = tr + 2 * mu * G[0][1][1]; P[2][2] = tr + 2 * mu * G[0][2][2];
@@ -81,7 +82,7 @@ struct PtLinear : MatBase {
     }
 };
 
-__device__ __forceinline__ void sym6_to_33(const double (&s)[6], double (&S)[3][3]) {
+JF_HD void sym6_to_33(const double (&s)[6], double (&S)[3][3]) {
     S[0][0] = s[0]; S[1][1] = s[1]; S[2][2] = s[2];
     S[0][1] = S[1][0] = s[3]; S[1][2] = S[2][1] = s[4]; S[0][2] = S[2][0] = s[5];
 }
@@ -91,7 +92,7 @@ __device__ __forceinline__ void sym6_to_33(const double (&s)[6], double (&S)[3][
 // (closed form of the Tensors.hessian call at neo_hookean.jl:222).  Total Lagrangian: P = F S,
 // dP = dF S + F (DD : sym(F' dF))  -- material + geometric stiffness (problems_elasticity.jl:270-289,378-404).
 struct NHCommon : MatBase {
-    __device__ __forceinline__ bool kin(const double (&Gu)[3][3], double (&F)[3][3], double (&Ci)[3][3], double &lnJ) const {
+    JF_HD bool kin(const double (&Gu)[3][3], double (&F)[3][3], double (&Ci)[3][3], double &lnJ) const {
         JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) F[i][j] = Gu[i][j] + (i == j ? 1.0 : 0.0);
         double C[3][3];
         JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) C[i][j] = F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j];
@@ -103,7 +104,7 @@ struct NHCommon : MatBase {
 
 struct PtNHResidual : NHCommon {
     static constexpr int NF = 1;
-    __device__ __forceinline__ bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
+    JF_HD bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
         double F[3][3], Ci[3][3], lnJ;
         bool ok = kin(G[0], F, Ci, lnJ);
         double S[3][3];
@@ -116,7 +117,7 @@ struct PtNHResidual : NHCommon {
 
 struct PtNHTangent : NHCommon {   // field 0 = v (direction), field 1 = u (linearisation point)
     static constexpr int NF = 2;
-    __device__ __forceinline__ bool eval(long long, const double (&G)[2][3][3], double (&P)[3][3]) const {
+    JF_HD bool eval(long long, const double (&G)[2][3][3], double (&P)[3][3]) const {
         double F[3][3], Ci[3][3], lnJ;
         bool ok = kin(G[1], F, Ci, lnJ);
         double c = la * lnJ - mu;
@@ -144,7 +145,7 @@ struct PPCommon : MatBase {
     const double *st_old;
     long long n_gp;
     // returns true if plastic; s = stress (tensor comps), n = flow direction s_trial/q, dl = plastic multiplier
-    __device__ __forceinline__ bool ret_map(long long gp, const double (&e)[6], double (&s)[6], double (&n)[6], double &dl) const {
+    JF_HD bool ret_map(long long gp, const double (&e)[6], double (&s)[6], double (&n)[6], double &dl) const {
         double ee[6], al[6];
         JF_UNROLL for (int i = 0; i < 6; i++) { ee[i] = e[i] - st_old[i * n_gp + gp]; al[i] = st_old[(6 + i) * n_gp + gp]; }
         double tr = la * (ee[0] + ee[1] + ee[2]);
@@ -165,7 +166,7 @@ struct PPCommon : MatBase {
     }
 };
 
-__device__ __forceinline__ void strain6(const double (&G)[3][3], double (&e)[6]) {
+JF_HD void strain6(const double (&G)[3][3], double (&e)[6]) {
     e[0] = G[0][0]; e[1] = G[1][1]; e[2] = G[2][2];
     e[3] = 0.5 * (G[0][1] + G[1][0]); e[4] = 0.5 * (G[1][2] + G[2][1]); e[5] = 0.5 * (G[0][2] + G[2][0]);
 }
@@ -173,7 +174,7 @@ __device__ __forceinline__ void strain6(const double (&G)[3][3], double (&e)[6])
 struct PtPPResidual : PPCommon {   // also writes the trial state (commit-on-convergence, abstract_material.jl:203-207)
     static constexpr int NF = 1;
     double *st_new;
-    __device__ __forceinline__ bool eval(long long gp, const double (&G)[1][3][3], double (&P)[3][3]) const {
+    JF_HD bool eval(long long gp, const double (&G)[1][3][3], double (&P)[3][3]) const {
         double e[6], s[6], n[6], dl;
         strain6(G[0], e);
         bool pl = ret_map(gp, e, s, n, dl);
@@ -192,7 +193,7 @@ struct PtPPResidual : PPCommon {   // also writes the trial state (commit-on-con
 
 struct PtPPTangent : PPCommon {   // field 0 = v, field 1 = u;  dP = DD_ep : sym(grad v)
     static constexpr int NF = 2;
-    __device__ __forceinline__ bool eval(long long gp, const double (&G)[2][3][3], double (&P)[3][3]) const {
+    JF_HD bool eval(long long gp, const double (&G)[2][3][3], double (&P)[3][3]) const {
         double e[6], s[6], n[6], dl, de[6], ds[6];
         strain6(G[1], e);
         bool pl = ret_map(gp, e, s, n, dl);
@@ -215,7 +216,7 @@ struct PtPPTangent : PPCommon {   // field 0 = v, field 1 = u;  dP = DD_ep : sym
 // X the coordinates; out(k, v0, v1, v2) receives the 3 components of node k of the element vector.  Returns false on invalid deformation.
 // ------------------------------------------------------------------------------------------------
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool tet10_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+JF_HD bool tet10_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
     Pt pt = pt0;
     pt.load(elem);
@@ -280,57 +281,77 @@ __device__ __forceinline__ bool tet10_general(const Pt &pt0, long long elem, con
 // (exact for the quadratic integrand) is replaced by its closed form on vertex values:
 //   G_c   = grad u at vertex c = 4 (u_c (x) g_c + sum_{a!=c} u_ac (x) g_a) - sum_a u_a (x) g_a ,  g_a = grad L_a
 //   f_a   = V/20 (4 sigma_a - S) g_a ,  f_ab = V/5 ((S + sigma_b) g_a + (S + sigma_a) g_b) ,  S = sum_c sigma_c
-// Only the 4 vertex coordinates are read.
+// Only the 4 vertex coordinates are read.  The constants are folded so that no stand-alone scaling multiplies remain:
+// with h = 4 g and t_c = V/20 sigma_c (Lame constants pre-scaled by V/20), T = sum t_c:
+//   G_c = u_c (x) h_c + sum_{a!=c} u_ac (x) h_a - W ,  f_a = (t_a - T/4) h_a ,  f_ab = (T + t_b) h_a + (T + t_a) h_b
+// (~520 fp64 instructions per element).
 // ------------------------------------------------------------------------------------------------
-template <class FLD, class OUT>
-__device__ __forceinline__ void tet10_affine_linear(double la, double mu, const FLD &U, const FLD &X, OUT &&out) {
-    double J[3][3], iJ[3][3];
+template <class FLD, class XFLD, class OUT>
+JF_HD void tet10_affine_linear(double la, double mu, const FLD &U, const XFLD &X, OUT &&out) {
+    double J[3][3];
     JF_UNROLL for (int a = 0; a < 3; a++) JF_UNROLL for (int c = 0; c < 3; c++) J[a][c] = X(a + 1, c) - X(0, c);
-    double det = inv3x3(J, iJ);
-    double g[4][3];
-    JF_UNROLL for (int j = 0; j < 3; j++) {
-        g[1][j] = iJ[j][0]; g[2][j] = iJ[j][1]; g[3][j] = iJ[j][2];
-        g[0][j] = -(iJ[j][0] + iJ[j][1] + iJ[j][2]);
+    // cofactors: cf[j][a] * (1/det) = d L_{a+1} / d x_j
+    double cf[3][3];
+    cf[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1]; cf[1][0] = J[1][2] * J[2][0] - J[1][0] * J[2][2]; cf[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    cf[0][1] = J[0][2] * J[2][1] - J[0][1] * J[2][2]; cf[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0]; cf[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
+    cf[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1]; cf[1][2] = J[0][2] * J[1][0] - J[0][0] * J[1][2]; cf[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double det = J[0][0] * cf[0][0] + J[0][1] * cf[1][0] + J[0][2] * cf[2][0];
+    const double r = 1.0 / det, r4 = 4.0 * r;
+    double W[3][3];   // sum_a u_a (x) g_a
+    {
+        double g[4][3];
+        JF_UNROLL for (int j = 0; j < 3; j++) {
+            g[1][j] = cf[j][0] * r; g[2][j] = cf[j][1] * r; g[3][j] = cf[j][2] * r;
+            g[0][j] = -(g[1][j] + g[2][j] + g[3][j]);
+        }
+        JF_UNROLL for (int i = 0; i < 3; i++) {
+            const double u0 = U(0, i), u1 = U(1, i), u2 = U(2, i), u3 = U(3, i);
+            JF_UNROLL for (int j = 0; j < 3; j++) W[i][j] = u0 * g[0][j] + u1 * g[1][j] + u2 * g[2][j] + u3 * g[3][j];
+        }
     }
-    double W[3][3];
-    JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
-        W[i][j] = U(0, i) * g[0][j] + U(1, i) * g[1][j] + U(2, i) * g[2][j] + U(3, i) * g[3][j];
-    double sg[4][6];   // vertex stresses, 11 22 33 12 23 13
+    double h[4][3];   // 4 grad L_a
+    JF_UNROLL for (int j = 0; j < 3; j++) {
+        h[1][j] = cf[j][0] * r4; h[2][j] = cf[j][1] * r4; h[3][j] = cf[j][2] * r4;
+        h[0][j] = -(h[1][j] + h[2][j] + h[3][j]);
+    }
+    const double v20 = det * (1.0 / 120.0), las = la * v20, mus = mu * v20, mus2 = mus + mus;
+    double t[4][6];   // V/20 * vertex stresses, 11 22 33 12 23 13
     JF_UNROLL for (int c = 0; c < 4; c++) {
         double G[3][3];
         JF_UNROLL for (int i = 0; i < 3; i++) {
-            double uc = 4.0 * U(c, i);
-            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] = uc * g[c][j] - W[i][j];
+            const double uc = U(c, i);
+            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] = uc * h[c][j] - W[i][j];
         }
         JF_UNROLL for (int a = 0; a < 4; a++) if (a != c) JF_UNROLL for (int i = 0; i < 3; i++) {
-            double ue = 4.0 * U(t10_edge(a, c), i);
-            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] += ue * g[a][j];
+            const double ue = U(t10_edge(a, c), i);
+            JF_UNROLL for (int j = 0; j < 3; j++) G[i][j] += ue * h[a][j];
         }
-        double tr = la * (G[0][0] + G[1][1] + G[2][2]);
-        sg[c][0] = tr + 2 * mu * G[0][0]; sg[c][1] = tr + 2 * mu * G[1][1]; sg[c][2] = tr + 2 * mu * G[2][2];
-        sg[c][3] = mu * (G[0][1] + G[1][0]); sg[c][4] = mu * (G[1][2] + G[2][1]); sg[c][5] = mu * (G[0][2] + G[2][0]);
+        const double tr = las * (G[0][0] + G[1][1] + G[2][2]);
+        t[c][0] = tr + mus2 * G[0][0]; t[c][1] = tr + mus2 * G[1][1]; t[c][2] = tr + mus2 * G[2][2];
+        t[c][3] = mus * (G[0][1] + G[1][0]); t[c][4] = mus * (G[1][2] + G[2][1]); t[c][5] = mus * (G[0][2] + G[2][0]);
     }
-    const double V = det * (1.0 / 6.0), v20 = V * (1.0 / 20.0), v5 = V * (1.0 / 5.0);
-    double S[6];
-    JF_UNROLL for (int q = 0; q < 6; q++) S[q] = sg[0][q] + sg[1][q] + sg[2][q] + sg[3][q];
-    auto mulsym = [](const double (&s)[6], const double (&v)[3], double (&r)[3]) {
-        r[0] = s[0] * v[0] + s[3] * v[1] + s[5] * v[2];
-        r[1] = s[3] * v[0] + s[1] * v[1] + s[4] * v[2];
-        r[2] = s[5] * v[0] + s[4] * v[1] + s[2] * v[2];
+    double T[6], Tq[6];
+    JF_UNROLL for (int q = 0; q < 6; q++) { T[q] = (t[0][q] + t[1][q]) + (t[2][q] + t[3][q]); Tq[q] = 0.25 * T[q]; }
+    auto mulsym = [](const double (&s)[6], const double (&v)[3], double (&o)[3]) {
+        o[0] = s[0] * v[0] + s[3] * v[1] + s[5] * v[2];
+        o[1] = s[3] * v[0] + s[1] * v[1] + s[4] * v[2];
+        o[2] = s[5] * v[0] + s[4] * v[1] + s[2] * v[2];
     };
     JF_UNROLL for (int a = 0; a < 4; a++) {
-        double m[6], r[3];
-        JF_UNROLL for (int q = 0; q < 6; q++) m[q] = v20 * (4.0 * sg[a][q] - S[q]);
-        mulsym(m, g[a], r);
-        out(a, r[0], r[1], r[2]);
+        double mm[6], o[3];
+        JF_UNROLL for (int q = 0; q < 6; q++) mm[q] = t[a][q] - Tq[q];
+        mulsym(mm, h[a], o);
+        out(a, o[0], o[1], o[2]);
     }
-    double Q[4][6];
-    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int q = 0; q < 6; q++) Q[a][q] = v5 * (S[q] + sg[a][q]);
+    JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int q = 0; q < 6; q++) t[a][q] += T[q];   // Q_a = T + t_a
     JF_UNROLL for (int a = 0; a < 4; a++) JF_UNROLL for (int b = a + 1; b < 4; b++) {
-        double r1[3], r2[3];
-        mulsym(Q[b], g[a], r1);
-        mulsym(Q[a], g[b], r2);
-        out(t10_edge(a, b), r1[0] + r2[0], r1[1] + r2[1], r1[2] + r2[2]);
+        const double (&qa)[6] = t[a];
+        const double (&qb)[6] = t[b];
+        double o[3];
+        o[0] = qb[0] * h[a][0] + qb[3] * h[a][1] + qb[5] * h[a][2] + qa[0] * h[b][0] + qa[3] * h[b][1] + qa[5] * h[b][2];
+        o[1] = qb[3] * h[a][0] + qb[1] * h[a][1] + qb[4] * h[a][2] + qa[3] * h[b][0] + qa[1] * h[b][1] + qa[4] * h[b][2];
+        o[2] = qb[5] * h[a][0] + qb[4] * h[a][1] + qb[2] * h[a][2] + qa[5] * h[b][0] + qa[4] * h[b][1] + qa[2] * h[b][2];
+        out(t10_edge(a, b), o[0], o[1], o[2]);
     }
 }
 
@@ -338,7 +359,7 @@ __device__ __forceinline__ void tet10_affine_linear(double la, double mu, const 
 // Tet4, GLTET1 (src/quadrature/gltet.jl:7-11): constant gradient.
 // ------------------------------------------------------------------------------------------------
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool tet4_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+JF_HD bool tet4_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
     Pt pt = pt0;
     pt.load(elem);
@@ -372,7 +393,7 @@ __device__ __forceinline__ bool tet4_general(const Pt &pt0, long long elem, cons
 // d/du at (.,v,w) = c1 + c4 v + c5 w + c7 v w, so the 8 Gauss-point gradients of a field cost ~60 flops
 // instead of 8 x 8 x 3.  Node order (-,-,-),(+,-,-),(+,+,-),(-,+,-),(-,-,+),... (lagrange_generated.jl:289-290).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hex8_modal(const double (&q)[8], double (&m)[8]) {
+JF_HD void hex8_modal(const double (&q)[8], double (&m)[8]) {
     // m = 1/8 * sum_i sign_i * q_i for monomials 1,u,v,w,uv,uw,vw,uvw
     double a0 = q[0] + q[1], a1 = q[1] - q[0], a2 = q[3] + q[2], a3 = q[2] - q[3];
     double a4 = q[4] + q[5], a5 = q[5] - q[4], a6 = q[7] + q[6], a7 = q[6] - q[7];
@@ -386,7 +407,7 @@ __device__ __forceinline__ void hex8_modal(const double (&q)[8], double (&m)[8])
 #define HEX_GA 0.5773502691896258
 
 template <class Pt, class FLD, class OUT>
-__device__ __forceinline__ bool hex8_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
+JF_HD bool hex8_general(const Pt &pt0, long long elem, const FLD (&F)[Pt::NF], const FLD &X, OUT &&out) {
     constexpr int NF = Pt::NF;
     Pt pt = pt0;
     pt.load(elem);

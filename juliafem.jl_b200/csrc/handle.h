@@ -20,6 +20,8 @@ struct jfem_handle {
     // options
     int patch_elems = 256;
     bool deterministic = true, affine = true, warp_specialised = true;
+    int debug_skip = 0;                 // profiling aid (option "debug_skip"): phases of the ws kernel to leave out
+    int lane_window = 48;               // candidates examined per lane by the bank-aware lane assignment (0 = off)
     // material
     int mat_kind = -1;
     double mat[4] = {0, 0, 0, 0};
@@ -32,9 +34,13 @@ struct jfem_handle {
     PatchSetHost hsets[N_CLASSES];
     InterfaceHost hif;
     PatchSetDev dsets[N_CLASSES];
-    DevBuf<uint32_t> inodes;
-    DevBuf<int32_t> iptr, islots, islot4;
-    DevBuf<double> ipart;
+    DevBuf<uint32_t> inodes;            // interface node ids, then the nodes no element touches
+    DevBuf<uint32_t> slot_node;         // partial slot -> node id
+    DevBuf<int32_t> ibase;              // first partial slot of each of those (+ end sentinel)
+    DevBuf<double> ipart;               // interface partials: 3 doubles per (interface node, touching patch)
+    DevBuf<unsigned int> gbar;          // grid-barrier arrival counter of the fused interface reduction
+    unsigned int gbar_count = 0;        // host mirror: counter value after the last launch
+    bool fused_iface = false, coop_ok = false;   // fused (cooperative-launch tail) variant measured slower than the separate kernel
     DevBuf<double> coords;
     DevBuf<uint8_t> fixed;              // per dof
     DevBuf<double> prescribed;          // per dof (values of fixed dofs)
@@ -91,8 +97,6 @@ struct jfem_handle {
     int ngp() const { return mesh.nnpe == 10 ? 4 : (mesh.nnpe == 8 ? 8 : 1); }
 };
 
-// modes of the element operator
-enum { OP_LINEAR = 0, OP_RESIDUAL = 1, OP_TANGENT = 2 };
 
 int ensure_built(jfem_handle *h);
 int op_apply(jfem_handle *h, int mode, const double *x_dev, double *y_dev, int flags, const int *done_flag);

@@ -2,18 +2,20 @@
 //
 // Elements are clustered spatially (recursive coordinate bisection of element centroids, leaves of
 // exactly EP elements) so that one thread block owns EP elements and the ~EP*nnpe/valence nodes they
-// touch.  For every patch we store (i) its unique node list (interface nodes -- those touched by more
-// than one patch -- first), (ii) the element->local-node table in node-major order (coalesced u16
-// reads), (iii) the element->staging-position table (node-major staging: all contributions to one node are
-// contiguous), which lets the kernel reduce
+// touch.  For every patch we store one metadata blob (layout in common.h): the node lists, the element table
+// (per element node: position of the node in the gathered x tile and the entry of the jagged staging tile that
+// receives the element's contribution) and the per-node reduce tables.  The staging tile lets the kernel reduce
 // element contributions per node in a FIXED order with no atomics (the deterministic replacement for
 // the 30 CUDA.@atomic adds of demos/gpu_assembly_tet10.jl:225-229 and the owner-computes gather of
-// ext/JuliaFEMCUDAExt.jl:293-361).  Interface nodes get one partial-sum slot per touching patch; a
-// second tiny kernel adds those in ascending patch order.
+// ext/JuliaFEMCUDAExt.jl:293-361).  Interface nodes (touched by more than one patch) get one partial-sum slot per
+// touching patch, contiguous per node; the last patch to arrive adds them in ascending patch order.
+// Elements are assigned to lanes so that the 16 lanes of a half-warp hit distinct shared-memory banks as often as
+// possible (greedy, windowed): the random 64-bit gathers / scatters of the element threads are the kernel's main cost.
 #include <algorithm>
 #include <cmath>
 #include <numeric>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -83,9 +85,85 @@ void classify_elements(MeshHost &m, bool use_affine) {
     }
 }
 
-int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost sets[N_CLASSES], InterfaceHost &iface) {
+namespace {
+
+// Per-patch work arrays of the lane assignment.  Access "slots" of an element thread: nnpe gathers of x (index = position
+// of the node in the x tile), nvx gathers of coordinates (index = coordinate slot) and nnpe scatters into the staging tile
+// (index = entry).  64-bit shared-memory accesses are served per half-warp; two lanes conflict when they address different
+// words of the same 8-byte bank (word index mod 16; the AoS factor 3 is a bijection mod 16).
+struct LaneOpt {
+    int ns = 0, ns_assign = 0;        // slots per element; leading slots the lane assignment looks at
+    std::vector<uint16_t> idx;        // [elem][slot]
+    int model(const std::vector<int> &perm, int ne, long long *per_slot = nullptr) const {   // modelled wavefronts (per component) of one patch
+        int total = 0;
+        for (int h0 = 0; h0 < ne; h0 += 16) {
+            int h1 = std::min(h0 + 16, ne);
+            for (int s = 0; s < ns; s++) {
+                uint16_t seen[16][16];
+                int nseen[16] = {0};
+                int mx = 1;
+                for (int t = h0; t < h1; t++) {
+                    uint16_t v = idx[(size_t)perm[t] * ns + s];
+                    int b = v & 15, k = 0;
+                    for (; k < nseen[b]; k++) if (seen[b][k] == v) break;
+                    if (k == nseen[b]) { seen[b][nseen[b]++] = v; mx = std::max(mx, nseen[b]); }
+                }
+                total += mx;
+                if (per_slot) per_slot[s] += mx;
+            }
+        }
+        return total;
+    }
+    // Greedy: fill one half-warp at a time; every lane takes, among the next `window` unassigned elements (caller order,
+    // so neighbours that share nodes -- broadcasts -- stay together), the one that raises the half-warp's wavefront
+    // count (sum over slots of the fullest bank) the least; ties go to fewer bank collisions, then to caller order.
+    void assign(std::vector<int> &perm, int ne, int window) const {
+        std::vector<uint8_t> used(ne, 0);
+        perm.resize(ne);
+        int first = 0, lane = 0;
+        std::vector<uint16_t> addr((size_t)ns * 16 * 16);   // distinct words per (slot, bank)
+        std::vector<uint8_t> cnt((size_t)ns * 16), mx(ns);
+        while (lane < ne) {
+            std::fill(cnt.begin(), cnt.end(), 0);
+            std::fill(mx.begin(), mx.end(), 0);
+            for (int s16 = 0; s16 < 16 && lane < ne; s16++) {
+                while (used[first]) first++;
+                int best = -1, bestcost = 1 << 30, seen = 0;
+                for (int i = first; i < ne && seen < window; i++) {
+                    if (used[i]) continue;
+                    seen++;
+                    const uint16_t *v = &idx[(size_t)i * ns];
+                    int cost = 0;
+                    for (int s = 0; s < ns_assign; s++) {
+                        const int sb = s * 16 + (v[s] & 15), n = cnt[sb];
+                        const uint16_t *ad = &addr[(size_t)sb * 16];
+                        int k = 0;
+                        for (; k < n; k++) if (ad[k] == v[s]) break;
+                        if (k == n && n > 0) cost += (n + 1 > mx[s]) ? 65 : 1;
+                    }
+                    if (cost < bestcost) { bestcost = cost; best = i; if (cost == 0) break; }
+                }
+                used[best] = 1;
+                perm[lane++] = best;
+                const uint16_t *v = &idx[(size_t)best * ns];
+                for (int s = 0; s < ns_assign; s++) {
+                    const int sb = s * 16 + (v[s] & 15), n = cnt[sb];
+                    uint16_t *ad = &addr[(size_t)sb * 16];
+                    int k = 0;
+                    for (; k < n; k++) if (ad[k] == v[s]) break;
+                    if (k == n) { ad[n] = v[s]; cnt[sb] = (uint8_t)(n + 1); if (n + 1 > mx[s]) mx[s] = (uint8_t)(n + 1); }
+                }
+            }
+        }
+    }
+};
+
+}  // namespace
+
+int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, PatchSetHost sets[N_CLASSES], InterfaceHost &iface) {
+    (void)use_affine;
     const int nnpe = m.nnpe;
-    if (EP * 3 * nnpe > 65535) { jfem_set_error("patch_elems=%d too large for 16-bit staging slots", EP); return JFEM_EINVAL; }
+    if (EP * nnpe > 65535) { jfem_set_error("patch_elems=%d too large for 16-bit staging entries", EP); return JFEM_EINVAL; }
     // centroids
     std::vector<double> cen(3 * (size_t)m.n_elems);
 #pragma omp parallel for schedule(static)
@@ -96,12 +174,14 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
             for (int d = 0; d < 3; d++) s[d] += m.coords[3 * (int64_t)m.conn[e * nnpe + k] + d];
         for (int d = 0; d < 3; d++) cen[3 * e + d] = s[d] / nv;
     }
+    // ---- pass 1: cluster the elements of each class into patches; unique node list (ascending id) per patch
     std::vector<int32_t> touch(m.n_nodes, 0);
-    int64_t elem_offset = 0;
+    std::vector<std::vector<int32_t>> pn[N_CLASSES];
     for (int c = 0; c < N_CLASSES; c++) {
         PatchSetHost &S = sets[c];
         S = PatchSetHost();
         S.cls = c; S.nnpe = nnpe; S.EP = EP;
+        S.nxr = (c == CLASS_AFFINE && nnpe == 10) ? 2 : 0;
         for (int64_t e = 0; e < m.n_elems; e++) if (m.cls[e] == c) S.elem_perm.push_back(e);
         S.n_elems = (int64_t)S.elem_perm.size();
         if (S.n_elems == 0) continue;
@@ -110,174 +190,264 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, PatchSetHost se
 #pragma omp single
         r.split(0, S.n_elems);
         S.n_patches = (int)((S.n_elems + EP - 1) / EP);
-        // keep caller order inside each patch (stable, deterministic)
+        pn[c].resize(S.n_patches);
 #pragma omp parallel for schedule(dynamic, 64)
         for (int p = 0; p < S.n_patches; p++) {
             int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
-            std::sort(S.elem_perm.begin() + lo, S.elem_perm.begin() + hi);
-        }
-        // unique nodes per patch
-        S.pnode_ptr.assign(S.n_patches + 1, 0);
-        std::vector<std::vector<int32_t>> pn(S.n_patches);
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int p = 0; p < S.n_patches; p++) {
-            int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
-            std::vector<int32_t> &v = pn[p];
+            std::sort(S.elem_perm.begin() + lo, S.elem_perm.begin() + hi);   // caller order inside each patch (deterministic)
+            std::vector<int32_t> &v = pn[c][p];
             v.reserve((hi - lo) * nnpe);
             for (int64_t i = lo; i < hi; i++)
                 for (int k = 0; k < nnpe; k++) v.push_back(m.conn[S.elem_perm[i] * nnpe + k]);
             std::sort(v.begin(), v.end());
             v.erase(std::unique(v.begin(), v.end()), v.end());
         }
+        S.pnode_ptr.assign(S.n_patches + 1, 0);
         for (int p = 0; p < S.n_patches; p++) {
-            if ((int)pn[p].size() > 65534) { jfem_set_error("patch has too many nodes"); return JFEM_EINVAL; }
-            S.pnode_ptr[p + 1] = S.pnode_ptr[p] + (int32_t)pn[p].size();
-            S.max_nodes = std::max(S.max_nodes, (int)pn[p].size());
-            for (int32_t n : pn[p]) touch[n]++;
+            if ((int)pn[c][p].size() > 65534) { jfem_set_error("patch has too many nodes"); return JFEM_EINVAL; }
+            S.pnode_ptr[p + 1] = S.pnode_ptr[p] + (int32_t)pn[c][p].size();
+            S.max_nodes = std::max(S.max_nodes, (int)pn[c][p].size());
+            for (int32_t n : pn[c][p]) touch[n]++;
         }
-        S.pnodes.resize(S.pnode_ptr[S.n_patches]);
-        for (int p = 0; p < S.n_patches; p++) std::copy(pn[p].begin(), pn[p].end(), S.pnodes.begin() + S.pnode_ptr[p]);
-        elem_offset += S.n_elems;
     }
-    // second pass: order patch nodes (interface first, then by descending incidence count so that the per-node
-    // gather loop has warp-uniform trip counts), build local tables
-    int64_t ipart_total = 0;
-    std::vector<std::vector<int32_t>> node_slots;  // filled below per interface node via sort
-    std::vector<std::pair<int32_t, int32_t>> ipairs; // (node, slot) in ascending (set, patch) order
+    // ---- interface nodes: contiguous partial slots per node; rank of every (patch, node) among the node's patches
+    iface = InterfaceHost();
+    std::vector<int32_t> ibase_of(m.n_nodes, -1);
+    {
+        int64_t tot = 0;
+        for (int64_t n = 0; n < m.n_nodes; n++) {
+            if (touch[n] > 255) { jfem_set_error("node %lld is shared by more than 255 patches", (long long)n); return JFEM_EINVAL; }
+            if (touch[n] > 1) {
+                iface.inodes.push_back((uint32_t)n);
+                iface.ibase.push_back((int32_t)tot);
+                ibase_of[n] = (int32_t)tot;
+                tot += touch[n];
+                if (tot > (int64_t)PN_ID_MASK) { jfem_set_error("too many interface partial slots"); return JFEM_EINVAL; }
+            } else if (touch[n] == 0) iface.orphans.push_back((uint32_t)n);
+        }
+        iface.n_partials = tot;
+    }
+    std::vector<uint8_t> prank[N_CLASSES];
+    {
+        std::vector<uint8_t> seen(m.n_nodes, 0);
+        for (int c = 0; c < N_CLASSES; c++) {
+            PatchSetHost &S = sets[c];
+            if (S.n_elems == 0) continue;
+            prank[c].resize(S.pnode_ptr[S.n_patches]);
+            for (int p = 0; p < S.n_patches; p++)
+                for (size_t j = 0; j < pn[c][p].size(); j++) prank[c][S.pnode_ptr[p] + j] = seen[pn[c][p][j]]++;
+        }
+    }
+    // ---- pass 2: per-patch tables and blobs
+    int overflow = 0;
     for (int c = 0; c < N_CLASSES; c++) {
         PatchSetHost &S = sets[c];
         if (S.n_elems == 0) continue;
-        S.n_iface.assign(S.n_patches, 0);
-        S.ipart_base.assign(S.n_patches, 0);
-        S.lconn.assign((size_t)S.n_patches * nnpe * EP, 0xFFFF);
-        S.goff.assign((size_t)S.pnode_ptr[S.n_patches] + S.n_patches, 0);
-        S.gslots.assign((size_t)S.n_patches * EP * nnpe, 0);
-        S.xslot.assign((size_t)S.pnode_ptr[S.n_patches], 0xFFFF);
-        std::vector<int> nxs(S.n_patches, 0);
+        const int nvx = S.nxr ? 4 : 0;
+        // sizes needed for the layout: max_nx, max_rows
+        std::vector<int> nxs(S.n_patches, 0), nrw(S.n_patches, 0);
 #pragma omp parallel for schedule(dynamic, 64)
         for (int p = 0; p < S.n_patches; p++) {
             int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
-            int nb = S.pnode_ptr[p], np = S.pnode_ptr[p + 1] - nb;
-            std::vector<int32_t> ids(S.pnodes.begin() + nb, S.pnodes.begin() + nb + np);  // ascending
-            std::vector<int32_t> cnt(np, 0);
-            std::vector<uint8_t> needx(np, 0);
-            auto local_of = [&](int32_t n) { return (int)(std::lower_bound(ids.begin(), ids.end(), n) - ids.begin()); };
+            const std::vector<int32_t> &ids = pn[c][p];
+            std::vector<int32_t> cnt(ids.size(), 0);
+            std::vector<uint8_t> nx(ids.size(), 0);
             for (int64_t i = lo; i < hi; i++)
                 for (int k = 0; k < nnpe; k++) {
-                    int j = local_of(m.conn[S.elem_perm[i] * nnpe + k]);
+                    int j = (int)(std::lower_bound(ids.begin(), ids.end(), m.conn[S.elem_perm[i] * nnpe + k]) - ids.begin());
                     cnt[j]++;
-                    if (c == CLASS_GENERAL || k < 4) needx[j] = 1;
+                    if (k < nvx) nx[j] = 1;
                 }
-            std::vector<int> order(np);
-            std::iota(order.begin(), order.end(), 0);
-            // Order of the patch nodes: interface nodes first (their partial slot is their position), then element
-            // VERTEX nodes before mid-side nodes (vertices collect ~3x more contributions, so warps of the per-node
-            // reduction get uniform trip counts), ascending id inside each class (locally consecutive addresses).
-            std::vector<uint8_t> isvert(np, 0);
-            for (int64_t i = lo; i < hi; i++)
-                for (int k = 0; k < (nnpe == 10 ? 4 : nnpe); k++) isvert[local_of(m.conn[S.elem_perm[i] * nnpe + k])] = 1;
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-                bool ia = touch[ids[a]] > 1, ib = touch[ids[b]] > 1;
-                if (ia != ib) return ia;
-                return isvert[a] > isvert[b];
-            });
-            std::vector<int> newpos(np);
-            int nif = 0;
-            for (int q = 0; q < np; q++) {
-                int j = order[q];
-                newpos[j] = q;
-                uint32_t w = (uint32_t)ids[j];
-                if (needx[j]) w |= PN_NEEDX;
-                if (touch[ids[j]] > 1) { w |= PN_IFACE; nif++; }
-                S.pnodes[nb + q] = w;
-            }
-            S.n_iface[p] = nif;
-            int nx = 0;
-            for (int q = 0; q < np; q++) if (S.pnodes[nb + q] & PN_NEEDX) S.xslot[nb + q] = (uint16_t)nx++;
-            nxs[p] = nx;
-            // offsets
-            uint16_t *go = &S.goff[(size_t)nb + p];
-            go[0] = 0;
-            for (int q = 0; q < np; q++) go[q + 1] = (uint16_t)(go[q] + cnt[order[q]]);
-            std::vector<int> fill(np);
-            for (int q = 0; q < np; q++) fill[q] = go[q];
-            uint16_t *gs = &S.gslots[(size_t)p * EP * nnpe];
-            for (int64_t i = lo; i < hi; i++) {
-                int t = (int)(i - lo);
-                for (int k = 0; k < nnpe; k++) {
-                    int q = newpos[local_of(m.conn[S.elem_perm[i] * nnpe + k])];
-                    S.lconn[((size_t)p * nnpe + k) * EP + t] = (uint16_t)q;
-                    gs[(size_t)k * EP + t] = (uint16_t)(fill[q]++ - go[q]);   // rank of this element among the node's contributions
-                }
-            }
+            nrw[p] = *std::max_element(cnt.begin(), cnt.end());
+            nxs[p] = (int)std::count(nx.begin(), nx.end(), (uint8_t)1);
         }
-        for (int p = 0; p < S.n_patches; p++) S.max_nx = std::max(S.max_nx, nxs[p]);
-        for (int p = 0; p < S.n_patches; p++) {
-            S.ipart_base[p] = (int32_t)ipart_total;
-            int nb = S.pnode_ptr[p];
-            for (int q = 0; q < S.n_iface[p]; q++) ipairs.emplace_back((int32_t)(S.pnodes[nb + q] & PN_ID_MASK), (int32_t)(ipart_total + q));
-            ipart_total += S.n_iface[p];
-            if (ipart_total > 0x7FFFFFF0LL) { jfem_set_error("too many interface partial slots"); return JFEM_EINVAL; }
-        }
-    }
-    // pack the per-patch blobs
-    bool rank_overflow = false;
-    for (int c = 0; c < N_CLASSES; c++) {
-        PatchSetHost &S = sets[c];
-        if (S.n_elems == 0) continue;
+        for (int p = 0; p < S.n_patches; p++) { S.max_nx = std::max(S.max_nx, nxs[p]); S.max_rows = std::max(S.max_rows, nrw[p]); }
+        if (S.max_rows > 255) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
+        S.max_entries = EP * nnpe;
         auto r16 = [](int v) { return (v + 15) & ~15; };
-        S.off_pn = 16;
-        S.off_xl = S.off_pn + r16(4 * S.max_nodes);
-        S.off_xs = S.off_xl + r16(4 * S.max_nx);
-        S.off_go = S.off_xs + r16(2 * S.max_nodes);
-        S.off_gs = S.off_go + r16(2 * (S.max_nodes + 1));
-        S.off_lc = S.off_gs + r16(EP * nnpe);
-        S.stride = S.off_lc + r16(2 * EP * nnpe);
-        S.blob.assign((size_t)S.stride * S.n_patches, 0);
-#pragma omp parallel for schedule(static)
+        PatchLayout &L = S.L;
+        L.offA = 0; L.off_pn = 16; L.off_xl = L.off_pn + r16(4 * S.max_nodes);
+        L.offB = L.off_xl + r16(4 * S.max_nx); L.off_et = L.offB + 16;
+        L.offC = L.off_et + r16(4 * (nnpe + S.nxr) * EP);
+        L.off_qn = L.offC + 16; L.off_ql = L.off_qn + r16(4 * S.max_nodes);
+        L.off_jo = L.off_ql + r16(S.max_nodes);
+        L.stride = L.off_jo + r16(2 * (S.max_rows + 1));
+        S.blob.assign((size_t)L.stride * S.n_patches, 0);
+        S.qnodes.assign((size_t)S.pnode_ptr[S.n_patches], 0);
+        S.qids.assign((size_t)S.pnode_ptr[S.n_patches], 0);
+        std::vector<int64_t> new_perm(S.elem_perm.size());
+        double wf0 = 0, wf1 = 0, wfi = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : wf0, wf1, wfi) reduction(| : overflow)
         for (int p = 0; p < S.n_patches; p++) {
-            uint8_t *b = &S.blob[(size_t)p * S.stride];
-            const int nb = S.pnode_ptr[p], np = S.pnode_ptr[p + 1] - nb;
+            const int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
+            const int ne = (int)(hi - lo);
+            const std::vector<int32_t> &ids = pn[c][p];
+            const int np = (int)ids.size(), nb = S.pnode_ptr[p];
+            auto local_of = [&](int32_t n) { return (int)(std::lower_bound(ids.begin(), ids.end(), n) - ids.begin()); };
+            std::vector<int32_t> cnt(np, 0);
+            std::vector<int32_t> xslot(np, -1);
+            std::vector<uint16_t> loc((size_t)ne * nnpe);
+            for (int i = 0; i < ne; i++)
+                for (int k = 0; k < nnpe; k++) {
+                    int j = local_of(m.conn[S.elem_perm[lo + i] * nnpe + k]);
+                    loc[(size_t)i * nnpe + k] = (uint16_t)j;
+                    cnt[j]++;
+                    if (k < nvx) xslot[j] = 0;
+                }
             int nx = 0;
-            uint32_t *xl = reinterpret_cast<uint32_t *>(b + S.off_xl);
-            for (int q = 0; q < np; q++) if (S.pnodes[nb + q] & PN_NEEDX) xl[nx++] = S.pnodes[nb + q] & PN_ID_MASK;
-            if ((S.n_iface[p] | nx) > 0xFFFF) nx = 0xFFFF;   // cannot happen: np <= 65534
-            int32_t hdr[4] = {np, S.n_iface[p] | (nx << 16), S.ipart_base[p], (int32_t)std::min<int64_t>(EP, S.n_elems - (int64_t)p * EP)};
-            memcpy(b, hdr, 16);
-            memcpy(b + S.off_pn, &S.pnodes[nb], 4 * (size_t)np);
-            memcpy(b + S.off_xs, &S.xslot[nb], 2 * (size_t)np);
-            memcpy(b + S.off_go, &S.goff[(size_t)nb + p], 2 * (size_t)(np + 1));
-            for (int q = 0; q < EP * nnpe; q++) {
-                uint16_t r = S.gslots[(size_t)p * EP * nnpe + q];
-                b[S.off_gs + q] = (uint8_t)(r > 255 ? 255 : r);
-                if (r > 255) rank_overflow = true;
+            for (int j = 0; j < np; j++) if (xslot[j] == 0) xslot[j] = nx++;
+            // reduce order q: descending contribution count, ascending id inside a count
+            std::vector<int> order(np), qpos(np);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+            for (int q = 0; q < np; q++) qpos[order[q]] = q;
+            const int nrows = cnt[order[0]];
+            std::vector<int> joff(nrows + 1, 0);
+            for (int r = 0; r < nrows; r++) {
+                int w = 0;
+                while (w < np && cnt[order[w]] > r) w++;   // np*nrows is small
+                joff[r + 1] = joff[r] + w;
             }
-            memcpy(b + S.off_lc, &S.lconn[(size_t)p * nnpe * EP], 2 * (size_t)EP * nnpe);
+            // ---- lane assignment (on the gather slots), then the staging rows.  Slot order: x gathers | coordinate gathers | scatters
+            LaneOpt lo_;
+            lo_.ns = 2 * nnpe + nvx;
+            lo_.ns_assign = nnpe + nvx;
+            lo_.idx.resize((size_t)ne * lo_.ns);
+            std::vector<uint16_t> ent((size_t)ne * nnpe);
+            {
+                std::vector<int> fill(np, 0);   // baseline: rank = caller order of the element inside the patch
+                for (int i = 0; i < ne; i++)
+                    for (int k = 0; k < nnpe; k++) {
+                        const int j = loc[(size_t)i * nnpe + k];
+                        const int e = joff[fill[j]++] + qpos[j];
+                        ent[(size_t)i * nnpe + k] = (uint16_t)e;
+                        lo_.idx[(size_t)i * lo_.ns + k] = (uint16_t)j;
+                        if (k < nvx) lo_.idx[(size_t)i * lo_.ns + nnpe + k] = (uint16_t)xslot[j];
+                        lo_.idx[(size_t)i * lo_.ns + nnpe + nvx + k] = (uint16_t)e;
+                    }
+            }
+            std::vector<int> perm(ne);
+            std::iota(perm.begin(), perm.end(), 0);
+            static long long dbg0[64], dbg1[64];
+            const bool dbg = getenv("JFEM_WF_DEBUG") != nullptr;
+            wf0 += lo_.model(perm, ne, dbg ? dbg0 : nullptr);
+            if (lane_window > 0) {
+                lo_.assign(perm, ne, lane_window);
+                // Staging rows: a node's contributions may take its rows in any order (the order only fixes the summation
+                // order).  Per half-warp and element node k, give every lane a free row of its node whose bank is still
+                // unused in that store instruction; most constrained nodes first.
+                std::vector<int> rstart(np + 1, 0);
+                for (int j = 0; j < np; j++) rstart[j + 1] = rstart[j] + cnt[j];
+                std::vector<uint8_t> rused(rstart[np], 0);
+                for (int h0 = 0; h0 < ne; h0 += 16) {
+                    const int h1 = std::min(h0 + 16, ne);
+                    for (int k = 0; k < nnpe; k++) {
+                        // bipartite matching lanes -> banks (augmenting paths); a lane may use bank b if its node has a free row there
+                        const int nl = h1 - h0;
+                        int jn[16], rowof[16][16], owner[16], got[16];
+                        for (int q = 0; q < nl; q++) {
+                            jn[q] = loc[(size_t)perm[h0 + q] * nnpe + k];
+                            got[q] = -1;
+                            for (int bb = 0; bb < 16; bb++) rowof[q][bb] = -1;
+                        }
+                        for (int bb = 0; bb < 16; bb++) owner[bb] = -1;
+                        // lanes sharing a node compete for its rows: hand each free row to one lane only (round-robin)
+                        for (int q = 0; q < nl; q++) {
+                            const int j = jn[q];
+                            int first = q, nshare = 0, myidx = 0;
+                            for (int q2 = 0; q2 < nl; q2++) if (jn[q2] == j) { if (q2 < first) first = q2; if (q2 < q) myidx++; nshare++; }
+                            int f = 0;
+                            for (int r = 0; r < cnt[j]; r++) {
+                                if (rused[rstart[j] + r]) continue;
+                                if (f++ % nshare != myidx) continue;
+                                const int bb = (joff[r] + qpos[j]) & 15;
+                                if (rowof[q][bb] < 0) rowof[q][bb] = r;
+                            }
+                        }
+                        for (int q = 0; q < nl; q++) {
+                            bool vis[16] = {false};
+                            struct Aug {
+                                static bool go(int q, int (*rowof)[16], int *owner, int *got, bool *vis) {
+                                    for (int bb = 0; bb < 16; bb++) {
+                                        if (rowof[q][bb] < 0 || vis[bb]) continue;
+                                        vis[bb] = true;
+                                        if (owner[bb] < 0 || go(owner[bb], rowof, owner, got, vis)) { owner[bb] = q; got[q] = bb; return true; }
+                                    }
+                                    return false;
+                                }
+                            };
+                            Aug::go(q, rowof, owner, got, vis);
+                        }
+                        int bank[16] = {0};
+                        for (int q = 0; q < nl; q++) if (got[q] >= 0) bank[got[q]]++;
+                        for (int pass = 0; pass < 2; pass++)   // matched lanes first, so that the others cannot take their rows
+                            for (int q = 0; q < nl; q++) {
+                                if ((got[q] >= 0) != (pass == 0)) continue;
+                                const int i = perm[h0 + q], j = jn[q];
+                                int br = -1;
+                                if (got[q] >= 0) br = rowof[q][got[q]];
+                                else {   // unmatched: least loaded bank among the node's free rows
+                                    int bc = 1 << 30;
+                                    for (int r = 0; r < cnt[j]; r++) {
+                                        if (rused[rstart[j] + r]) continue;
+                                        const int c2 = bank[(joff[r] + qpos[j]) & 15];
+                                        if (c2 < bc) { bc = c2; br = r; }
+                                    }
+                                    bank[(joff[br] + qpos[j]) & 15]++;
+                                }
+                                rused[rstart[j] + br] = 1;
+                                const int e = joff[br] + qpos[j];
+                                ent[(size_t)i * nnpe + k] = (uint16_t)e;
+                                lo_.idx[(size_t)i * lo_.ns + nnpe + nvx + k] = (uint16_t)e;
+                            }
+                    }
+                }
+            }
+            wf1 += lo_.model(perm, ne, dbg ? dbg1 : nullptr);
+            if (dbg && p == S.n_patches - 1) {
+                for (int k = 0; k < lo_.ns; k++) fprintf(stderr, "%.2f ", dbg0[k] / (16.0 * S.n_patches));
+                fprintf(stderr, "\n");
+                for (int k = 0; k < lo_.ns; k++) fprintf(stderr, "%.2f ", dbg1[k] / (16.0 * S.n_patches));
+                fprintf(stderr, "\n");
+            }
+            wfi += lo_.ns * ((ne + 15) / 16);
+            for (int t = 0; t < ne; t++) new_perm[lo + t] = S.elem_perm[lo + perm[t]];
+            // ---- write the blob
+            uint8_t *b = &S.blob[(size_t)p * L.stride];
+            const int32_t hdr[4] = {np, nx, ne, nrows};
+            memcpy(b + L.offA, hdr, 16); memcpy(b + L.offB, hdr, 16); memcpy(b + L.offC, hdr, 16);
+            uint32_t *bpn = reinterpret_cast<uint32_t *>(b + L.off_pn), *bxl = reinterpret_cast<uint32_t *>(b + L.off_xl);
+            uint32_t *bet = reinterpret_cast<uint32_t *>(b + L.off_et);
+            uint32_t *bqn = reinterpret_cast<uint32_t *>(b + L.off_qn);
+            uint8_t *bql = b + L.off_ql;
+            uint16_t *bjo = reinterpret_cast<uint16_t *>(b + L.off_jo);
+            for (int j = 0; j < np; j++) {
+                bpn[j] = (uint32_t)ids[j];
+                if (xslot[j] >= 0) bxl[xslot[j]] = (uint32_t)ids[j];
+            }
+            for (int t = 0; t < ne; t++) {
+                const int i = perm[t];
+                for (int k = 0; k < nnpe; k++) bet[(size_t)k * EP + t] = (uint32_t)loc[(size_t)i * nnpe + k] | ((uint32_t)ent[(size_t)i * nnpe + k] << 16);
+                for (int k = 0; k < nvx; k += 2)
+                    bet[(size_t)(nnpe + k / 2) * EP + t] =
+                        (uint32_t)xslot[loc[(size_t)i * nnpe + k]] | ((uint32_t)xslot[loc[(size_t)i * nnpe + k + 1]] << 16);
+            }
+            for (int q = 0; q < np; q++) {
+                const int j = order[q];
+                const int32_t n = ids[j];
+                // interior node: its id (the sum is stored to y); interface node: the partial slot of this (patch, node)
+                uint32_t w = touch[n] > 1 ? (PN_IFACE | (uint32_t)(ibase_of[n] + (int32_t)prank[c][nb + j])) : (uint32_t)n;
+                if (cnt[j] > 255) overflow |= 1;
+                bqn[q] = w;
+                bql[q] = (uint8_t)cnt[j];
+                S.qnodes[nb + q] = w;
+                S.qids[nb + q] = n;
+            }
+            for (int r = 0; r <= nrows; r++) bjo[r] = (uint16_t)joff[r];
         }
-        std::vector<uint16_t>().swap(S.lconn);
-        std::vector<uint16_t>().swap(S.gslots);
-        std::vector<uint16_t>().swap(S.goff);
-        std::vector<uint16_t>().swap(S.xslot);
+        S.elem_perm.swap(new_perm);
+        S.wf_before = wf0 / S.n_patches; S.wf_after = wf1 / S.n_patches; S.wf_ideal = wfi / S.n_patches;
     }
-    if (rank_overflow) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
-    // interface node -> partial slots (ascending slot = ascending (set, patch))
-    std::stable_sort(ipairs.begin(), ipairs.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) { return a.first < b.first; });
-    iface = InterfaceHost();
-    iface.n_partials = ipart_total;
-    iface.iptr.push_back(0);
-    for (size_t i = 0; i < ipairs.size(); i++) {
-        if (i == 0 || ipairs[i].first != ipairs[i - 1].first) {
-            if (i) iface.iptr.push_back((int32_t)i);
-            iface.inodes.push_back((uint32_t)ipairs[i].first);
-        }
-        iface.islots.push_back(ipairs[i].second);
-    }
-    if (!ipairs.empty()) iface.iptr.push_back((int32_t)ipairs.size());
-    // nodes no element touches: listed with an empty slot range so that the reduce kernel stores y = 0 for them
-    for (int64_t n = 0; n < m.n_nodes; n++)
-        if (touch[n] == 0) {
-            iface.inodes.push_back((uint32_t)n);
-            iface.iptr.push_back((int32_t)ipairs.size());
-        }
+    if (overflow) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
     return JFEM_OK;
 }

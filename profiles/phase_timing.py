@@ -1,11 +1,15 @@
 """Debug aid: clock64 stamps of block 0 of the warp-specialised patch kernel (option "debug_timing"):
 compute warp 0 / helper warp 0, first 7 patches."""
-import sys, ctypes as C, numpy as np, torch
+import os, sys, ctypes as C, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from juliafem.jl_b200 import _lib, mesh
-m = mesh.tet10_kuhn(88, 22, 22, 4.0, 1.0, 1.0)
+dims = [int(v) for v in os.environ.get('JFEM_DIMS', '88,22,22').split(',')]
+m = mesh.tet10_kuhn(dims[0], dims[1], dims[2], 4.0, 1.0, 1.0)
 h = _lib.Handle(10, m.coords, m.conn); h.set_material(0, (210e9, 0.3))
 h.set_option("debug_timing", 1)
+import os
+h.set_option("debug_skip", int(os.environ.get("JFEM_SKIP", "0")))
+print("debug_skip =", os.environ.get("JFEM_SKIP", "0"))
 x = torch.from_numpy(mesh.test_vector(m.n_dofs)).cuda(); y = torch.empty_like(x)
 h.set_stream(torch.cuda.current_stream().cuda_stream)
 flush = torch.empty(128 * 1024 * 1024, dtype=torch.float32, device='cuda')
@@ -22,4 +26,4 @@ for k in range(3):
         print(f"compute it {it} start {r[0]-base:6d} blobwait {max(r[5]-r[0],0):5d} ldg-issue {r[1]-max(r[5],r[0]):5d} stage_empty-wait {r[2]-r[1]:5d} ph1 {r[3]-r[2]:5d} store+sync {r[4]-r[3]:5d}")
     for it in range(7):
         r = hp[it]
-        print(f"helper  it {it} start {r[0]-base:6d} wait {r[1]-r[0]:5d} ph2 {r[2]-r[1]:5d}")
+        print(f"helper  it {it} start {r[0]-base:6d} wait {r[1]-r[0]:5d} ph2 {r[2]-r[1]:5d} (lens {r[3]-r[1]:5d} rows {r[4]-r[3]:5d} [{r[6]} rows] stores {r[2]-r[4]:5d})")

@@ -1,0 +1,122 @@
+// hostcheck.cu -- TEST INFRASTRUCTURE (never loaded by the product): runs the patch pipeline of csrc/matvec.cu on the
+// CPU, using the very tables patches.cpp builds and the same element code (patch_elem.cuh / elem.cuh compiled for the
+// host).  It validates the blob layout (gather order, element table, jagged staging entries, reduce order, interface
+// slots) without a GPU; the kernels' synchronisation is of course only exercised by the -m gpu tests.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../juliafem.jl_b200/csrc/patch_elem.cuh"
+
+static char g_err[512];
+void jfem_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+using namespace jf;
+
+template <int NNPE, int CLS, int T>
+static void run_set(const PatchSetHost &S, long long elem_offset, const MeshHost &m, const PtLinear &pt, const double *x, double *y, int project,
+                    std::vector<double> &ipart) {
+    const PatchLayout &L = S.L;
+    const bool x_all = S.nxr == 0;
+    std::vector<double> xs(3 * (size_t)S.max_nodes), Xs(3 * (size_t)(x_all ? S.max_nodes : S.max_nx)), stage(3 * (size_t)S.max_entries);
+    for (int p = 0; p < S.n_patches; p++) {
+        const uint8_t *b = &S.blob[(size_t)p * L.stride];
+        const int32_t *hdr = reinterpret_cast<const int32_t *>(b);
+        const int np = hdr[0], nx = hdr[1], ne = hdr[2], nrows = hdr[3];
+        const uint32_t *pn = reinterpret_cast<const uint32_t *>(b + L.off_pn), *xl = reinterpret_cast<const uint32_t *>(b + L.off_xl);
+        const uint32_t *et = reinterpret_cast<const uint32_t *>(b + L.off_et);
+        const uint32_t *qn = reinterpret_cast<const uint32_t *>(b + L.off_qn);
+        const uint8_t *ql = b + L.off_ql;
+        const uint16_t *jo = reinterpret_cast<const uint16_t *>(b + L.off_jo);
+        for (int j = 0; j < np; j++)
+            for (int c = 0; c < 3; c++) {
+                xs[3 * j + c] = x[3 * (size_t)pn[j] + c];
+                if (x_all) Xs[3 * j + c] = m.coords[3 * (size_t)pn[j] + c];
+            }
+        if (!x_all)
+            for (int j = 0; j < nx; j++)
+                for (int c = 0; c < 3; c++) Xs[3 * j + c] = m.coords[3 * (size_t)xl[j] + c];
+        std::fill(stage.begin(), stage.end(), 1e300);   // poison: every entry read must have been written
+        for (int t = 0; t < ne; t++)
+            element_phase<NNPE, CLS, OP_LINEAR, PtLinear, T>(pt, elem_offset + (long long)p * T + t, et, t, xs.data(), Xs.data(), nullptr, stage.data());
+        (void)nrows;
+        for (int q = 0; q < np; q++) {
+            const uint32_t w = qn[q];
+            const int len = ql[q];
+            for (int c = 0; c < 3; c++) {
+                double s = 0.0;
+                for (int r = 0; r < len; r++) s += stage[3 * ((size_t)jo[r] + q) + c];
+                if (project && ((w >> (PN_FIXSHIFT + c)) & 1u)) s = 0.0;
+                if (w & PN_IFACE) ipart[3 * (size_t)(w & PN_ID_MASK) + c] = s;
+                else y[3 * (size_t)(w & PN_ID_MASK) + c] = s;
+            }
+        }
+    }
+}
+
+extern "C" const char *hostcheck_error() { return g_err; }
+
+// y = K x through the patch tables, on the CPU.  conn 0-based.  stats[8]: wf_before, wf_after, wf_ideal, n_patches,
+// n_interface_nodes, blob stride, n_partials, n_affine
+extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, const double *coords, const int32_t *conn, const uint8_t *fixed, int EP,
+                                int lane_window, int use_affine, double E, double nu, const double *x, double *y, int project, double *stats) {
+    MeshHost m;
+    m.nnpe = nnpe; m.n_nodes = n_nodes; m.n_elems = n_elems;
+    m.coords.assign(coords, coords + 3 * n_nodes);
+    m.conn.assign(conn, conn + (size_t)nnpe * n_elems);
+    m.fixed.assign(fixed, fixed + 3 * n_nodes);
+    classify_elements(m, use_affine != 0);
+    PatchSetHost sets[N_CLASSES];
+    InterfaceHost hif;
+    if (build_patch_sets(m, EP, use_affine != 0, lane_window, sets, hif) != JFEM_OK) return 1;
+    // embed the Dirichlet mask exactly like upload_fixed()
+    for (int c = 0; c < N_CLASSES; c++) {
+        PatchSetHost &S = sets[c];
+        for (int p = 0; p < S.n_patches; p++) {
+            uint32_t *qn = reinterpret_cast<uint32_t *>(&S.blob[(size_t)p * S.L.stride + S.L.off_qn]);
+            for (int q = 0, nb = S.pnode_ptr[p]; q < S.pnode_ptr[p + 1] - nb; q++) {
+                uint32_t w = S.qnodes[nb + q] & ~(7u << PN_FIXSHIFT);
+                const long long id = S.qids[nb + q];
+                for (int d = 0; d < 3; d++)
+                    if (m.fixed[3 * id + d]) w |= (1u << (PN_FIXSHIFT + d));
+                qn[q] = w;
+            }
+        }
+    }
+    PtLinear pt;
+    pt.la = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)); pt.mu = E / (2.0 * (1.0 + nu)); pt.sy = 0; pt.H = 0; pt.pe = nullptr; pt.pe_n = 0;
+    for (long long i = 0; i < 3 * n_nodes; i++) y[i] = 1e300;   // poison: every dof must be written
+    for (uint32_t n : hif.orphans) y[3 * (size_t)n] = y[3 * (size_t)n + 1] = y[3 * (size_t)n + 2] = 0.0;
+    std::vector<double> ipart(3 * (size_t)hif.n_partials + 3, 1e300);
+    long long off = 0;
+    for (int c = 0; c < N_CLASSES; c++) {
+        const PatchSetHost &S = sets[c];
+        if (S.n_elems == 0) continue;
+#define RUN(N, C, TT) run_set<N, C, TT>(S, off, m, pt, x, y, project, ipart)
+#define RUN_T(N, C) do { if (EP == 128) RUN(N, C, 128); else if (EP == 256) RUN(N, C, 256); else RUN(N, C, 512); } while (0)
+        if (nnpe == 10) { if (c == CLASS_AFFINE) RUN_T(10, CLASS_AFFINE); else RUN_T(10, CLASS_GENERAL); }
+        else if (nnpe == 8) RUN_T(8, CLASS_GENERAL);
+        else RUN_T(4, CLASS_AFFINE);
+        off += S.n_elems;
+    }
+    // interface nodes: slots in ascending (set, patch) order, like iface_reduce_kernel
+    for (size_t i = 0; i < hif.inodes.size(); i++) {
+        const long long b0 = hif.ibase[i], b1 = i + 1 < hif.inodes.size() ? hif.ibase[i + 1] : hif.n_partials;
+        for (int c = 0; c < 3; c++) {
+            double v = 0.0;
+            for (long long r = b0; r < b1; r++) v += ipart[3 * (size_t)r + c];
+            y[3 * (size_t)hif.inodes[i] + c] = v;
+        }
+    }
+    const PatchSetHost &M = sets[CLASS_AFFINE].n_elems ? sets[CLASS_AFFINE] : sets[CLASS_GENERAL];
+    stats[0] = M.wf_before; stats[1] = M.wf_after; stats[2] = M.wf_ideal;
+    stats[3] = sets[0].n_patches + sets[1].n_patches; stats[4] = (double)hif.inodes.size(); stats[5] = M.L.stride;
+    stats[6] = (double)hif.n_partials; stats[7] = (double)sets[CLASS_AFFINE].n_elems;
+    return 0;
+}
