@@ -206,9 +206,11 @@ __device__ __forceinline__ void reduce_patch_ilp(const PatchKArgs &a, const unsi
         // rows r < len[m] belong to chain m; a finished chain reads the zero word instead (address select, no predicated
         // loads: predicates are scarce and serialise the chains).  Loop bounds are warp-uniform maxima; the chain set
         // shrinks in four steps (lens are sorted: len[0] >= len[1] >= ...).
-        auto rows = [&](auto nchain, auto unroll, int upto) {
+        // warp-uniform loop bounds: lane 0 holds the warp's first node of every chain, i.e. (sorted order) the longest
+        const unsigned lens4 = __shfl_sync(full, (unsigned)len[5] | ((unsigned)len[2] << 8) | ((unsigned)len[1] << 16) | ((unsigned)len[0] << 24), 0);
+        auto rows = [&](auto nchain, auto unroll, int lim) {
             constexpr int NC = decltype(nchain)::value, UN = decltype(unroll)::value;
-            const int lim = (a.dbg & 2) ? 0 : __reduce_max_sync(full, upto);
+            if (a.dbg & 2) lim = 0;
 #pragma unroll UN
             for (; r < lim; r++) {
                 const double *row = sp + 3 * jo[r];
@@ -220,10 +222,10 @@ __device__ __forceinline__ void reduce_patch_ilp(const PatchKArgs &a, const unsi
         };
         using std::integral_constant;
         static_assert(MC >= 6, "chain steps assume at least six chains");
-        rows(integral_constant<int, MC>(), integral_constant<int, 1>(), len[5]);   // until chains 5.. are complete
-        rows(integral_constant<int, 5>(), integral_constant<int, 2>(), len[2]);    // until chains 2..4 are complete
-        rows(integral_constant<int, 2>(), integral_constant<int, 4>(), len[1]);
-        rows(integral_constant<int, 1>(), integral_constant<int, 8>(), len[0]);
+        rows(integral_constant<int, MC>(), integral_constant<int, 2>(), (int)(lens4 & 255u));          // until chains 5.. are complete
+        rows(integral_constant<int, 5>(), integral_constant<int, 2>(), (int)((lens4 >> 8) & 255u));    // until chains 2..4 are complete
+        rows(integral_constant<int, 2>(), integral_constant<int, 4>(), (int)((lens4 >> 16) & 255u));
+        rows(integral_constant<int, 1>(), integral_constant<int, 8>(), (int)(lens4 >> 24));
         if (tm) { tm[4] = clock64(); tm[6] = r; }
         if (a.dbg & 1) continue;
         // stores, branch-free: all table lookups first, then one (predicated) store per chain
@@ -509,6 +511,9 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
 // Nodes no element touches are listed with an empty slot range (y = 0).
 __global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const int32_t *__restrict__ ibase, const double *__restrict__ ipart,
                                     double *__restrict__ y, long long n3, const int *done) {
+    // launched with programmatic stream serialisation: the grid may be set up while the patch kernel drains; everything
+    // the patch kernel wrote is visible after this call
+    cudaGridDependencySynchronize();
     if (done && *done) return;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n3) iface_item(inodes, ibase, ipart, y, i);
@@ -784,7 +789,14 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         JFEM_TRY(rc);
     }
     if (!atomic_iface && n3 && !fused) {
-        iface_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, h->stream>>>(h->inodes.p, h->ibase.p, h->ipart.p, y, n3, done);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((n3 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        JFEM_CUDA(cudaLaunchKernelEx(&cfg, iface_reduce_kernel, (const uint32_t *)h->inodes.p, (const int32_t *)h->ibase.p, (const double *)h->ipart.p, y, n3,
+                                     done));
         JFEM_CUDA(cudaGetLastError());
         h->matvec_launches++;
     }
