@@ -204,7 +204,7 @@ def main():
         step()
     barrier()
     info = h.info()
-    launches_per_step = int(info.matvec_launches) + (2 if world > 1 else 0)
+    launches_before = int(info.total_launches)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -218,6 +218,7 @@ def main():
         step()
         ev[k][1].record()
     barrier()
+    launches_timed = int(h.info().total_launches) - launches_before     # kernels of the library launched inside the timed region
     times = np.array([a.elapsed_time(b) for a, b in ev])       # ms, device time of each step
     ms = float(times.mean())
     if world > 1:
@@ -278,11 +279,12 @@ def main():
                        "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
                        "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems), "smem_bytes": int(info.smem_bytes), "blocks_per_sm": int(info.blocks_per_sm), "interface_nodes": int(info.n_interface_nodes),
                        "partition": ("z-slabs by contiguous node range, owner-computes + ghost elements; halo via "
-                                     + ("ncclSend/ncclRecv" if args.nccl_halo else "peer-memory stores over NVLink (CUDA IPC)")) if world > 1 else "single GPU",
+                                     + ("ncclSend/ncclRecv" if args.nccl_halo else "peer-memory stores over NVLink (CUDA IPC) issued from inside the patch kernel; "
+                                        "patches that read ghost values run last and wait for the neighbours' flags")) if world > 1 else "single GPU",
                        "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds)},
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
                     "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_timed,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_per_dof": BYTES_PER_DOF[et],
                          "note": "achieved = algorithmic bytes of one K.u / CUDA-event time of the whole step (patch kernel + interface reduce)"},

@@ -127,6 +127,8 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         else h->timing.release();
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
+    } else if (!strcmp(key, "fused_halo")) {
+        h->fused_halo = value != 0;
     } else if (!strcmp(key, "fused_interface")) {
         h->fused_iface = value != 0;
     } else if (!strcmp(key, "debug_skip")) {
@@ -257,7 +259,7 @@ int jfem_matvec(jfem_handle *h, const double *x, double *y, int flags, int on_de
     const double *dx; double *dy;
     JFEM_TRY(in_vec(h, x, on_device, h->wx, &dx));
     JFEM_TRY(out_vec_begin(h, y, on_device, h->wy, &dy));
-    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, (double *)dx));
+    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, (double *)dx, !(flags & JFEM_USE_CSR)));
     if (flags & JFEM_USE_CSR) JFEM_TRY(csr_spmv(h, dx, dy, flags, nullptr));
     else JFEM_TRY(op_apply(h, (flags & JFEM_TANGENT) ? OP_TANGENT : OP_LINEAR, dx, dy, flags, nullptr));
     JFEM_TRY(out_vec_end(h, y, on_device, dy));
@@ -271,7 +273,7 @@ int jfem_internal_force(jfem_handle *h, const double *u, double *f, int flags, i
     const double *du; double *df;
     JFEM_TRY(in_vec(h, u, on_device, h->wx, &du));
     JFEM_TRY(out_vec_begin(h, f, on_device, h->wy, &df));
-    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, (double *)du));
+    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, (double *)du, true));
     JFEM_TRY(op_apply(h, OP_RESIDUAL, du, df, flags, nullptr));
     JFEM_TRY(out_vec_end(h, f, on_device, df));
     return check_domain(h, on_device, "internal force");

@@ -220,7 +220,7 @@ int vec_dot(jfem_handle *h, const double *a, const double *b, double *out_host) 
 }
 
 static int apply_operator(jfem_handle *h, int flags, double *x, double *y, const int *done) {
-    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, x));
+    if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, x, !(flags & JFEM_USE_CSR)));
     if (flags & JFEM_USE_CSR) return csr_spmv(h, x, y, flags | JFEM_PROJECT, done);
     return op_apply(h, (flags & JFEM_TANGENT) ? OP_TANGENT : OP_LINEAR, x, y, flags | JFEM_PROJECT, done);
 }
@@ -307,7 +307,7 @@ int newton_krylov(jfem_handle *h, const double *fext, double *u, double newton_t
     int total_cg = 0, it = 0;
     double Rn = 0;
     for (it = 0; it <= max_newton; it++) {
-        if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, u));
+        if (h->n_ranks > 1) JFEM_TRY(halo_exchange(h, u, true));
         JFEM_TRY(op_apply(h, OP_RESIDUAL, u, h->nk_f.p, 0, nullptr));
         axpby_kernel<<<blocks, thr, 0, h->stream>>>(n, 1.0, fext, -1.0, h->nk_f.p, h->nk_R.p, h->fixed.p);
         JFEM_CUDA(cudaGetLastError());

@@ -126,9 +126,30 @@ __global__ void halo_pull_kernel(P2PArgs a, const double *__restrict__ land, con
     }
 }
 
-static int halo_exchange_p2p(jfem_handle *h, double *x) {
+// the exchange the next patch kernel performs itself (sequence number already advanced by halo_exchange)
+void halo_fill_fused(jfem_handle *h, HaloFused &f) {
+    const int nnb = (int)h->nb_rank.size();
+    const int par = (int)(h->p2p_seq & 1);
+    f.n_nb = nnb;
+    for (int i = 0; i < nnb; i++) {
+        f.peer_land[i] = h->p2p_peer_land[i] + (size_t)par * h->p2p_peer_half[i] + 3 * h->p2p_peer_off[i];
+        f.peer_flag[i] = h->p2p_peer_flag[i];
+        f.my_flag[i] = h->p2p_flags.p + h->nb_rank[i];
+    }
+    for (int i = 0; i <= nnb; i++) f.send_off[i] = h->send_ptr[i];
+    f.send_nodes = h->send_nodes.p;
+    f.land = h->p2p_land.p + (size_t)par * h->p2p_half;
+    f.seq = h->p2p_seq;
+    f.ticket = h->p2p_ticket.p;
+}
+
+static int halo_exchange_p2p(jfem_handle *h, double *x, bool fused_ok) {
     const int nnb = (int)h->nb_rank.size();
     h->p2p_seq++;
+    if (fused_ok && h->fused_halo && h->recv_contiguous && ws_halo_capable(h)) {   // the next op_apply(x) pushes / waits / reads the landing buffer itself
+        h->halo_armed = true; h->halo_x = x;
+        return JFEM_OK;
+    }
     const int par = (int)(h->p2p_seq & 1);
     P2PArgs a;
     a.n_nb = nnb;
@@ -261,9 +282,9 @@ int comm_allreduce_sum(jfem_handle *h, double *buf, int count) {
 }
 
 // forward halo: owned interface values of x -> neighbours' ghost slots
-int halo_exchange(jfem_handle *h, double *x) {
+int halo_exchange(jfem_handle *h, double *x, bool fused_ok) {
     if (h->n_ranks <= 1 || h->nb_rank.empty()) return JFEM_OK;
-    if (h->p2p_ready) return halo_exchange_p2p(h, x);
+    if (h->p2p_ready) return halo_exchange_p2p(h, x, fused_ok);
     const int nnb = (int)h->nb_rank.size();
     const long long ns3 = 3 * h->send_ptr[nnb], nr3 = 3 * h->recv_ptr[nnb];
     if (ns3) halo_pack_kernel<<<(unsigned)((ns3 + 255) / 256), 256, 0, h->stream>>>(ns3, h->send_nodes.p, x, h->send_buf.p);
@@ -299,6 +320,7 @@ extern "C" int jfem_comm_init(jfem_handle *h, int n_ranks, int rank, const char 
     memcpy(id.internal, id128, 128);
     JFEM_NCCL(N.init_rank(&h->comm, n_ranks, id, rank));
     h->n_ranks = n_ranks; h->rank = rank; h->n_owned_nodes = n_owned_nodes;
+    h->built = false;   // the patch order depends on which nodes are ghosts
     return JFEM_OK;
 }
 
@@ -312,6 +334,8 @@ extern "C" int jfem_comm_set_halo(jfem_handle *h, int nnb, const int32_t *nb_ran
     std::vector<int32_t> s(send_nodes, send_nodes + send_ptr[nnb]), r(recv_nodes, recv_nodes + recv_ptr[nnb]);
     for (auto &v : s) { v -= h->index_base; if (v < 0 || v >= h->mesh.n_nodes) { jfem_set_error("halo send node out of range"); return JFEM_EINVAL; } }
     for (auto &v : r) { v -= h->index_base; if (v < 0 || v >= h->mesh.n_nodes) { jfem_set_error("halo recv node out of range"); return JFEM_EINVAL; } }
+    h->recv_contiguous = h->n_owned_nodes >= 0;
+    for (size_t i = 0; i < r.size() && h->recv_contiguous; i++) h->recv_contiguous = r[i] == (int64_t)h->n_owned_nodes + (int64_t)i;
     JFEM_TRY(h->send_nodes.upload(s));
     JFEM_TRY(h->recv_nodes.upload(r));
     JFEM_TRY(h->send_buf.alloc(3 * s.size() + 1));

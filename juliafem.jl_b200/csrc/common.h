@@ -67,7 +67,7 @@ struct DevBuf {
 };
 
 // Per-patch metadata blob (what the kernels stream into shared memory by TMA bulk copies).  Three parts with different
-// lifetimes inside the kernel, each starting with the same 16-byte header {np, nx, ne, nrows}:
+// lifetimes inside the kernel, each starting with the same 16-byte header {np, nx, ne, nrows | ghost flag << 16}:
 //   part A  gather lists      pn u32[max_nodes]  node ids in GATHER order p (ascending id: coalesced loads of x)
 //                             xl u32[max_nx]     ids of the nodes whose coordinates are needed (affine Tet10: the
 //                                                element vertices; empty when every node needs them -> pn is used)
@@ -102,6 +102,7 @@ struct PatchSetHost {
     std::vector<int32_t> pnode_ptr;    // n_patches+1
     std::vector<uint32_t> qnodes;      // node words in reduce order (kept to re-embed the Dirichlet mask)
     std::vector<int32_t> qids;         // node id of every entry of qnodes
+    std::vector<uint8_t> ghosty;       // per patch: reads ghost values (nodes >= n_owned of a partitioned mesh)
     PatchLayout L;
     std::vector<uint8_t> blob;
     // layout statistics (modelled shared-memory wavefronts of the element threads per patch, before / after lane assignment)
@@ -136,5 +137,5 @@ struct MeshHost {
     std::vector<uint8_t> cls;       // per element class
 };
 
-int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, PatchSetHost sets[N_CLASSES], InterfaceHost &iface);
+int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, int64_t n_owned, PatchSetHost sets[N_CLASSES], InterfaceHost &iface);
 void classify_elements(MeshHost &m, bool use_affine);

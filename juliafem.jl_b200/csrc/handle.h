@@ -87,6 +87,11 @@ struct jfem_handle {
     std::vector<double *> p2p_peer_land;
     std::vector<unsigned long long *> p2p_peer_flag, p2p_ctrl;
     unsigned long long p2p_ar_seq = 0;
+    bool fused_halo = true;             // option "fused_halo": exchange inside the patch kernel when the ws kernel runs
+    bool recv_contiguous = false;       // ghost node g receives into landing slot g - n_owned
+    bool halo_armed = false;            // halo_exchange() deferred the exchange to the next op_apply on halo_x
+    const double *halo_x = nullptr;
+    bool halo_in_kernel = false;        // the last exchange ran inside the patch kernel (statistics)
     std::vector<int64_t> p2p_peer_off;
     std::vector<size_t> p2p_peer_half;
     // stats
@@ -98,9 +103,25 @@ struct jfem_handle {
 };
 
 
+// Arguments of the halo exchange fused into the patch kernel (peer-memory stores over NVLink, see comm.cu / matvec.cu)
+struct HaloFused {
+    int n_nb;
+    double *peer_land[8];               // neighbour's landing buffer (mapped), offset to MY segment and this exchange's half
+    unsigned long long *peer_flag[8];   // neighbour's flag word for me
+    const unsigned long long *my_flag[8];
+    long long send_off[9];              // node offsets of the per-neighbour send segments
+    const int32_t *send_nodes;
+    const double *land;                 // my landing half of this exchange: 3 doubles per ghost node, in ghost order
+    unsigned long long seq;
+    unsigned int *ticket;
+};
+
 int ensure_built(jfem_handle *h);
+bool ws_halo_capable(jfem_handle *h);
+void halo_fill_fused(jfem_handle *h, HaloFused &f);
 int op_apply(jfem_handle *h, int mode, const double *x_dev, double *y_dev, int flags, const int *done_flag);
-int halo_exchange(jfem_handle *h, double *x_dev);
+// fused_ok: the caller applies the patch operator to x next, so the exchange may be carried by that kernel
+int halo_exchange(jfem_handle *h, double *x_dev, bool fused_ok = false);
 int comm_allreduce_sum(jfem_handle *h, double *buf_dev, int count);
 int upload_fixed(jfem_handle *h);
 int upload_material(jfem_handle *h);

@@ -47,6 +47,12 @@ struct PatchKArgs {
     const uint32_t *inodes;
     const int32_t *ibase;
     long long n_inodes3;
+    // halo exchange fused into the ws kernel (partitioned meshes): the helper warps push this rank's interface values into
+    // the neighbours' landing buffers during the pipeline prologue; patches that read ghost values are ordered last and
+    // wait for the neighbours' flags; ghost values are read straight from the landing buffer.
+    int halo;
+    uint32_t n_owned;          // nodes >= n_owned are ghosts (0xFFFFFFFF: none)
+    HaloFused hf;
 };
 
 // y[interface node] = sum of its partial slots (contiguous, ascending (set, patch) order); item = (node, component).
@@ -403,15 +409,33 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         double rx[WS_GN][3], rc[GC][3];
         JF_UNROLL for (int r = 0; r < WS_GN; r++) rx[r][0] = rx[r][1] = rx[r][2] = 0.0;
         JF_UNROLL for (int r = 0; r < GC; r++) rc[r][0] = rc[r][1] = rc[r][2] = 0.0;
+        bool halo_seen = !a.halo;
+        // value of node id: owned nodes from x; ghost nodes from the landing buffer the neighbours wrote (volatile: the
+        // same addresses are rewritten every second exchange, so the read must not hit a stale L1 line)
+        auto node_ptr = [&](uint32_t id, bool &ghost) -> const double * {
+            ghost = id >= a.n_owned;
+            return ghost ? a.hf.land + 3 * (long long)(id - a.n_owned) : a.x + 3 * (long long)id;
+        };
         auto load_regs = [&](const unsigned char *pa) {
             const int *hdr = reinterpret_cast<const int *>(pa);
             const int np = (a.dbg & 8) ? 0 : hdr[0], nx = (a.dbg & 8) ? 0 : (a.x_all ? np : hdr[1]);
+            if (!halo_seen && (hdr[3] & 0x10000)) {   // first patch that reads ghost values: the neighbours' data must have landed
+                if (tid < a.hf.n_nb) {
+                    const volatile unsigned long long *f = a.hf.my_flag[tid];
+                    while (*f < a.hf.seq) { }
+                }
+                named_sync(3, WS_T);
+                __threadfence_system();
+                halo_seen = true;
+            }
             const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
             const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
             JF_UNROLL for (int r = 0; r < WS_GN; r++) {
                 const int j = tid + r * T;
-                const double *g = a.x + 3 * (long long)pn[j < np ? j : 0];
-                rx[r][0] = __ldg(g); rx[r][1] = __ldg(g + 1); rx[r][2] = __ldg(g + 2);
+                bool ghost;
+                const double *g = node_ptr(pn[j < np ? j : 0], ghost);
+                if (ghost) { rx[r][0] = __ldcv(g); rx[r][1] = __ldcv(g + 1); rx[r][2] = __ldcv(g + 2); }
+                else { rx[r][0] = __ldg(g); rx[r][1] = __ldg(g + 1); rx[r][2] = __ldg(g + 2); }
             }
             JF_UNROLL for (int r = 0; r < GC; r++) {
                 const int j = tid + r * T;
@@ -434,8 +458,10 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
             const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
             const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
             for (int j = tid + WS_GN * T; j < np; j += T) {
-                const double *g = a.x + 3 * (long long)pn[j];
-                xs[3 * j] = __ldg(g); xs[3 * j + 1] = __ldg(g + 1); xs[3 * j + 2] = __ldg(g + 2);
+                bool ghost;
+                const double *g = node_ptr(pn[j], ghost);
+                if (ghost) { xs[3 * j] = __ldcv(g); xs[3 * j + 1] = __ldcv(g + 1); xs[3 * j + 2] = __ldcv(g + 2); }
+                else { xs[3 * j] = __ldg(g); xs[3 * j + 1] = __ldg(g + 1); xs[3 * j + 2] = __ldg(g + 2); }
             }
             for (int j = tid + GC * T; j < nx; j += T) {
                 const double *g = a.coords + 3 * (long long)xl[j];
@@ -488,6 +514,27 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         // =========================== helper warps ===========================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_HELPER_REGS));
         const int hid = threadIdx.x - WS_T;
+        if (a.halo) {
+            // push this rank's interface values into the neighbours' landing buffers (all helper threads of all blocks),
+            // fence, and let the last block to finish publish the sequence flags -- while the compute warps fill the pipeline
+            const long long n3 = 3 * a.hf.send_off[a.hf.n_nb];
+            for (long long i = (long long)blockIdx.x * WS_H + hid; i < n3; i += (long long)gridDim.x * WS_H) {
+                const long long q = i / 3;
+                int nb = 0;
+                while (q >= a.hf.send_off[nb + 1]) nb++;
+                a.hf.peer_land[nb][i - 3 * a.hf.send_off[nb]] = a.x[3LL * a.hf.send_nodes[q] + (i - 3 * q)];
+            }
+            __threadfence_system();
+            named_sync(1, WS_H);
+            if (hid == 0) {
+                const unsigned int t = atomicAdd(a.hf.ticket, 1u);
+                if (t == gridDim.x - 1) {
+                    *a.hf.ticket = 0;
+                    __threadfence_system();
+                    for (int nb = 0; nb < a.hf.n_nb; nb++) *((volatile unsigned long long *)a.hf.peer_flag[nb]) = a.hf.seq;
+                }
+            }
+        }
         for (int k = 0; k < n_it; k++) {
             const bool tm = a.timing && blockIdx.x == 0 && hid == 0 && k < 8;
             if (tm) a.timing[64 + k * 8 + 0] = clock64();
@@ -570,7 +617,7 @@ int ensure_built(jfem_handle *h) {
     JFEM_CUDA(cudaSetDevice(h->device));
     auto t0 = std::chrono::steady_clock::now();
     classify_elements(h->mesh, h->affine);
-    JFEM_TRY(build_patch_sets(h->mesh, h->patch_elems, h->affine, h->lane_window, h->hsets, h->hif));
+    JFEM_TRY(build_patch_sets(h->mesh, h->patch_elems, h->affine, h->lane_window, h->n_ranks > 1 ? h->n_owned_nodes : -1, h->hsets, h->hif));
     h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     int64_t off = 0;
     std::vector<int64_t> e2i(h->mesh.n_elems);
@@ -628,6 +675,21 @@ int ensure_built(jfem_handle *h) {
 
 // ------------------------------------------------------------------------------------------------ launch
 
+static bool ws_layout(const PatchSetDev &D, int x_all, WsSmem &L) {
+    auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    const size_t xtile = sizeof(double) * 3 * (size_t)(x_all ? D.max_nodes : D.max_nx);
+    L.strideA = (int)r128(D.L.bytesA()); L.strideB = (int)r128(D.L.bytesB()); L.strideC = (int)r128(D.L.bytesC());
+    L.A = 128;
+    L.B = L.A + 2 * L.strideA;
+    L.C = L.B + 2 * L.strideB;
+    L.stage = L.C + 2 * L.strideC;
+    L.xs = (int)r128(L.stage + 2 * sizeof(double) * 3 * (size_t)D.max_entries);
+    L.Xs = (int)r128(L.xs + 2 * sizeof(double) * 3 * D.max_nodes);
+    L.total = (int)r128(L.Xs + 2 * xtile);
+    return L.total <= 227 * 1024;
+}
+
+
 template <int NNPE, int CLS, int MODE, class Pt, int T>
 static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const Pt &pt) {
     constexpr int NF = Pt::NF;
@@ -636,15 +698,7 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
     if constexpr (MODE == OP_LINEAR && T == WS_T && NF == 1 && NNPE == 10 && CLS == CLASS_AFFINE) {
         if (h->warp_specialised) {
             WsSmem L;
-            L.strideA = (int)r128(a.bytesA); L.strideB = (int)r128(a.bytesB); L.strideC = (int)r128(a.bytesC);
-            L.A = 128;
-            L.B = L.A + 2 * L.strideA;
-            L.C = L.B + 2 * L.strideB;
-            L.stage = L.C + 2 * L.strideC;
-            L.xs = (int)r128(L.stage + 2 * sizeof(double) * 3 * (size_t)D.max_entries);
-            L.Xs = (int)r128(L.xs + 2 * sizeof(double) * 3 * D.max_nodes);
-            L.total = (int)r128(L.Xs + 2 * xtile);
-            if (L.total <= 227 * 1024) {
+            if (ws_layout(D, a.x_all, L)) {
                 constexpr int GC = (CLS == CLASS_AFFINE && NNPE == 10) ? 1 : WS_GN;
                 auto kws = patch_kernel_ws<NNPE, CLS, MODE, Pt, GC>;
                 static int configured_ws = 0;
@@ -747,6 +801,16 @@ static int dispatch_threads(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, 
     return JFEM_EINVAL;
 }
 
+// true when op_apply will run exactly one warp-specialised patch kernel (which can carry the halo exchange)
+bool ws_halo_capable(jfem_handle *h) {
+    if (ensure_built(h) != JFEM_OK) return false;
+    if (h->mesh.nnpe != 10 || h->mat_kind != JFEM_MAT_LINEAR_ELASTIC || !h->warp_specialised || h->patch_elems != WS_T) return false;
+    const PatchSetDev &D = h->dsets[CLASS_AFFINE];
+    if (h->dsets[CLASS_GENERAL].n_elems != 0 || D.n_elems == 0) return false;
+    WsSmem L;
+    return ws_layout(D, D.nxr == 0 ? 1 : 0, L);
+}
+
 // y = A(x): mode OP_LINEAR (K x), OP_RESIDUAL (f_int(x)), OP_TANGENT (K(ulin) x)
 int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, const int *done) {
     JFEM_TRY(ensure_built(h));
@@ -771,6 +835,14 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         PatchKArgs a;
         a.tail = (fused && c == last_set) ? 1 : 0;   // the last patch kernel of the operator also reduces the interface nodes
         a.gbar = h->gbar.p; a.gbar_target = 0; a.inodes = h->inodes.p; a.ibase = h->ibase.p; a.n_inodes3 = n3;
+        a.halo = 0; a.n_owned = 0xFFFFFFFFu;
+        if (h->halo_armed) {
+            if (x != h->halo_x) { jfem_set_error("internal: fused halo armed for another vector"); return JFEM_ESTATE; }
+            a.halo = 1; a.n_owned = (uint32_t)h->n_owned_nodes;
+            halo_fill_fused(h, a.hf);
+            h->halo_armed = false;
+            h->halo_in_kernel = true;
+        }
         a.blob = D.blob.p; a.n_patches = D.n_patches; a.stride = L.stride;
         a.offB = L.offB; a.offC = L.offC; a.bytesA = L.bytesA(); a.bytesB = L.bytesB(); a.bytesC = L.bytesC();
         a.a_pn = L.off_pn - L.offA; a.a_xl = L.off_xl - L.offA; a.b_et = L.off_et - L.offB;

@@ -160,7 +160,7 @@ struct LaneOpt {
 
 }  // namespace
 
-int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, PatchSetHost sets[N_CLASSES], InterfaceHost &iface) {
+int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, int64_t n_owned, PatchSetHost sets[N_CLASSES], InterfaceHost &iface) {
     (void)use_affine;
     const int nnpe = m.nnpe;
     if (EP * nnpe > 65535) { jfem_set_error("patch_elems=%d too large for 16-bit staging entries", EP); return JFEM_EINVAL; }
@@ -201,6 +201,28 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                 for (int k = 0; k < nnpe; k++) v.push_back(m.conn[S.elem_perm[i] * nnpe + k]);
             std::sort(v.begin(), v.end());
             v.erase(std::unique(v.begin(), v.end()), v.end());
+        }
+        // Partitioned meshes (nodes >= n_owned are ghosts whose values arrive by the halo exchange): patches that read no
+        // ghost value come first, so that the kernel can start on them while the halo is still in flight.  The partial
+        // patch (if any) stays last: the internal element order is patch-major with full patches.
+        S.ghosty.assign(S.n_patches, 0);
+        if (n_owned >= 0 && n_owned < m.n_nodes) {
+            for (int p = 0; p < S.n_patches; p++) S.ghosty[p] = pn[c][p].back() >= n_owned ? 1 : 0;   // ids ascending
+            const int nfull = (int)(S.n_elems / EP);
+            std::vector<int> ord(nfull);
+            std::iota(ord.begin(), ord.end(), 0);
+            std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return S.ghosty[a] < S.ghosty[b]; });
+            std::vector<int64_t> ep2(S.elem_perm.size());
+            std::vector<std::vector<int32_t>> pn2(S.n_patches);
+            std::vector<uint8_t> gh2(S.n_patches, 0);
+            for (int q = 0; q < S.n_patches; q++) {
+                const int p = q < nfull ? ord[q] : q;
+                const int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
+                std::copy(S.elem_perm.begin() + lo, S.elem_perm.begin() + hi, ep2.begin() + (int64_t)q * EP);
+                pn2[q].swap(pn[c][p]);
+                gh2[q] = S.ghosty[p];
+            }
+            S.elem_perm.swap(ep2); pn[c].swap(pn2); S.ghosty.swap(gh2);
         }
         S.pnode_ptr.assign(S.n_patches + 1, 0);
         for (int p = 0; p < S.n_patches; p++) {
@@ -414,7 +436,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
             for (int t = 0; t < ne; t++) new_perm[lo + t] = S.elem_perm[lo + perm[t]];
             // ---- write the blob
             uint8_t *b = &S.blob[(size_t)p * L.stride];
-            const int32_t hdr[4] = {np, nx, ne, nrows};
+            const int32_t hdr[4] = {np, nx, ne, nrows | (S.ghosty[p] ? 0x10000 : 0)};   // bit 16: the patch reads ghost values
             memcpy(b + L.offA, hdr, 16); memcpy(b + L.offB, hdr, 16); memcpy(b + L.offC, hdr, 16);
             uint32_t *bpn = reinterpret_cast<uint32_t *>(b + L.off_pn), *bxl = reinterpret_cast<uint32_t *>(b + L.off_xl);
             uint32_t *bet = reinterpret_cast<uint32_t *>(b + L.off_et);

@@ -28,7 +28,7 @@ static void run_set(const PatchSetHost &S, long long elem_offset, const MeshHost
     for (int p = 0; p < S.n_patches; p++) {
         const uint8_t *b = &S.blob[(size_t)p * L.stride];
         const int32_t *hdr = reinterpret_cast<const int32_t *>(b);
-        const int np = hdr[0], nx = hdr[1], ne = hdr[2], nrows = hdr[3];
+        const int np = hdr[0], nx = hdr[1], ne = hdr[2], nrows = hdr[3] & 0xFFFF;
         const uint32_t *pn = reinterpret_cast<const uint32_t *>(b + L.off_pn), *xl = reinterpret_cast<const uint32_t *>(b + L.off_xl);
         const uint32_t *et = reinterpret_cast<const uint32_t *>(b + L.off_et);
         const uint32_t *qn = reinterpret_cast<const uint32_t *>(b + L.off_qn);
@@ -65,7 +65,7 @@ extern "C" const char *hostcheck_error() { return g_err; }
 // y = K x through the patch tables, on the CPU.  conn 0-based.  stats[8]: wf_before, wf_after, wf_ideal, n_patches,
 // n_interface_nodes, blob stride, n_partials, n_affine
 extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, const double *coords, const int32_t *conn, const uint8_t *fixed, int EP,
-                                int lane_window, int use_affine, double E, double nu, const double *x, double *y, int project, double *stats) {
+                                int lane_window, int use_affine, double E, double nu, const double *x, double *y, int project, double *stats, long long n_owned) {
     MeshHost m;
     m.nnpe = nnpe; m.n_nodes = n_nodes; m.n_elems = n_elems;
     m.coords.assign(coords, coords + 3 * n_nodes);
@@ -74,7 +74,7 @@ extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, 
     classify_elements(m, use_affine != 0);
     PatchSetHost sets[N_CLASSES];
     InterfaceHost hif;
-    if (build_patch_sets(m, EP, use_affine != 0, lane_window, sets, hif) != JFEM_OK) return 1;
+    if (build_patch_sets(m, EP, use_affine != 0, lane_window, n_owned, sets, hif) != JFEM_OK) return 1;
     // embed the Dirichlet mask exactly like upload_fixed()
     for (int c = 0; c < N_CLASSES; c++) {
         PatchSetHost &S = sets[c];

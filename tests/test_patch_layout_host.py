@@ -23,11 +23,11 @@ def hostcheck():
     L.hostcheck_error.restype = C.c_char_p
     L.hostcheck_matvec.restype = C.c_int
     L.hostcheck_matvec.argtypes = [C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                   C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+                                   C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong]
     return L
 
 
-def run(L, m, x, fixed=None, EP=256, window=48, affine=1, project=0, E=210e9, nu=0.3):
+def run(L, m, x, fixed=None, EP=256, window=48, affine=1, project=0, E=210e9, nu=0.3, n_owned=-1):
     coords = np.ascontiguousarray(m.coords, dtype=np.float64)
     conn = np.ascontiguousarray(m.conn - 1, dtype=np.int32)
     fx = np.zeros(m.n_dofs, dtype=np.uint8)
@@ -37,7 +37,7 @@ def run(L, m, x, fixed=None, EP=256, window=48, affine=1, project=0, E=210e9, nu
     stats = np.zeros(8)
     x = np.ascontiguousarray(x, dtype=np.float64)
     rc = L.hostcheck_matvec(m.elem_type, m.n_nodes, m.n_elems, coords.ctypes.data, conn.ctypes.data, fx.ctypes.data, EP, window, affine, E, nu,
-                            x.ctypes.data, y.ctypes.data, project, stats.ctypes.data)
+                            x.ctypes.data, y.ctypes.data, project, stats.ctypes.data, n_owned)
     assert rc == 0, L.hostcheck_error().decode()
     return y, stats
 
@@ -104,3 +104,12 @@ def test_lane_assignment_reduces_modelled_conflicts(hostcheck, jf):
     before, after, ideal = st[0], st[1], st[2]
     assert ideal <= after < before
     print(f"modelled 64-bit shared-memory wavefronts per patch and component: {before:.0f} -> {after:.0f} (ideal {ideal:.0f})")
+
+
+def test_ghost_aware_patch_order(hostcheck, oracle, jf):
+    """Partitioned mesh: patches that read ghost nodes (ids >= n_owned) are ordered last; results unchanged."""
+    m = jf.mesh.tet10_kuhn(10, 5, 5, 2.0, 1.0, 1.0)
+    u = jf.mesh.test_vector(m.n_dofs)
+    n_owned = int(0.8 * m.n_nodes)
+    y, st = run(hostcheck, m, u, n_owned=n_owned)
+    assert relerr(y, oracle.matfree(10, m.coords, m.conn, u, par=(210e9, 0.3))) < 1e-12
