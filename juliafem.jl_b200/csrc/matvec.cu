@@ -362,10 +362,6 @@ struct WsSmem {   // byte offsets inside dynamic shared memory, computed on the 
 template <int NNPE, int CLS, int MODE, class Pt, int GC>
 __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, Pt pt, WsSmem L) {
     extern __shared__ __align__(128) unsigned char sm[];
-    if (a.done && *a.done) {
-        if (a.tail && threadIdx.x == 0) atomicAdd(a.gbar, 1u);
-        return;
-    }
     constexpr int T = WS_T;
     uint64_t *mb = reinterpret_cast<uint64_t *>(sm);
     uint64_t *A_full = mb, *B_full = mb + 2, *C_full = mb + 4, *stage_full = mb + 6, *stage_empty = mb + 8;
@@ -399,6 +395,12 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         if (n_it > 0) reqB(0);
     }
     __syncthreads();
+    if (a.done && *a.done) {   // device-side convergence flag of the CG loop: nothing to do; let the requested copies land first
+        for (int k = 0; k < 2 && k < n_it; k++) { mbar_wait(&A_full[k], 0); mbar_wait(&C_full[k], 0); }
+        if (n_it > 0) mbar_wait(&B_full[0], 0);
+        if (a.tail && threadIdx.x == 0) atomicAdd(a.gbar, 1u);
+        return;
+    }
 
     if (threadIdx.x < WS_T) {
         // =========================== compute warps ===========================
@@ -712,8 +714,12 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
                     a.gbar_target = (h->gbar_count += (unsigned)grid);
                     void *args[] = {(void *)&a, (void *)&pt, (void *)&L};
                     JFEM_CUDA(cudaLaunchCooperativeKernel((const void *)kws, dim3(grid), dim3(WS_T + WS_H), args, (size_t)L.total, h->stream));
-                } else
+                } else {
+                    // (launching this kernel itself with programmatic stream serialisation was measured: -4 % per CG
+                    // iteration on T1 but +10 % on T10, where the early-resident persistent blocks starve the tail of
+                    // the preceding vector kernel -- not used)
                     kws<<<grid, WS_T + WS_H, L.total, h->stream>>>(a, pt, L);
+                }
                 JFEM_CUDA(cudaGetLastError());
                 h->matvec_launches++;
                 return JFEM_OK;
