@@ -85,7 +85,11 @@ int jfem_create(jfem_handle **out, int device, int elem_type, int64_t n_nodes, i
                 const double *coords, const int32_t *conn, int index_base);
 int jfem_destroy(jfem_handle *h);
 /* tuning knobs, before the first operator call: "patch_elems" (elements per thread-block patch),
- * "deterministic" (1: ordered interface reduction [default], 0: fp64 atomics), "affine_fast_path" (1/0) */
+ * "deterministic" (1: ordered interface reduction [default], 0: fp64 atomics), "affine_fast_path" (1/0),
+ * "warp_specialised" (1/0), "lane_window" (candidates per lane of the bank-aware lane assignment, 0 = off),
+ * "fused_halo" (1: halo exchange inside the patch kernel when peer mappings exist [default]),
+ * "fused_interface" (1: cooperative-launch in-kernel interface reduction; default 0, measured slower),
+ * profiling aids "debug_timing", "debug_skip" */
 int jfem_set_option(jfem_handle *h, const char *key, double value);
 /* homogeneous material (per_element == 0: params has n_params entries, 2 <= n_params <= 4) or per-element
  * (per_element != 0: params is n_params x n_elems column-major), like E_vec/nu_vec of ext:135-141 */
