@@ -59,7 +59,7 @@ def nccl_main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     et = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    m = mesh.tet10_kuhn(8, 3, 6, 4.0, 1.0, 2.0) if et == 10 else mesh.hex8_lattice(9, 8, 13, 0.1)
+    m = mesh.tet10_kuhn(16, 6, 12, 4.0, 1.0, 2.0) if et == 10 else mesh.hex8_lattice(9, 8, 13, 0.1)
     fixed = mesh.clamp_dofs(m)
     u = mesh.test_vector(m.n_dofs, fixed)
     b = np.zeros(m.n_dofs); b[2::3] = -1e3
@@ -71,8 +71,10 @@ def nccl_main():
     # partitioned
     pp = PartitionedProblem(m, rank, world, lr, fixed_dofs=fixed)
     pp.init_comm(torch_broadcast_bytes(dist, dev))
-    if len(sys.argv) > 3 and sys.argv[3] == "p2p":
+    if len(sys.argv) > 3 and sys.argv[3].startswith("p2p"):
         pp.init_p2p(torch_all_gather_object(dist))
+        if sys.argv[3] == "p2p-unfused":
+            pp.handle.set_option("fused_halo", 0)          # separate push / pull kernels instead of the in-kernel exchange
     ul = pp.scatter_vector(u)
     ul[3 * pp.n_owned:] = 1e300                               # ghosts must be overwritten by the halo exchange
     xd = torch.from_numpy(ul).to(dev)

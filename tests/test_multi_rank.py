@@ -35,7 +35,7 @@ def test_gloo_world2_halo_and_allreduce(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("halo", ["nccl", "p2p"])
+@pytest.mark.parametrize("halo", ["nccl", "p2p", "p2p-unfused"])
 @pytest.mark.parametrize("et", [10, 8])
 def test_nccl_two_gpus_matvec_and_cg(et, halo):
     import torch
@@ -47,5 +47,5 @@ def test_nccl_two_gpus_matvec_and_cg(et, halo):
     line = [l for l in r.stdout.splitlines() if l.startswith("MULTIRANK_RESULT")]
     assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
     e_mv, e_cg, it2, it1 = [float(v) for v in line[0].split()[1:]]
-    assert e_mv < 1e-12          # owned rows of K.u identical to the single-GPU result
+    assert e_mv < 1e-12          # owned rows of K.u identical to the single-GPU result (p2p + Tet10: halo fused into the patch kernel)
     assert e_cg < 1e-6 and abs(it2 - it1) <= max(3, it1 // 50)
