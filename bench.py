@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--workload", default="T1", choices=sorted(WORKLOADS))
     ap.add_argument("--patch", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (jfem_set_option), repeatable")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
     ap.add_argument("--cg", action="store_true", help="also time a full CG solve (||r|| <= 1e-8 ||b||) on the workload")
@@ -177,7 +178,7 @@ def main():
     fixed_g = mesh.clamp_dofs(m)
     total_dofs = m.n_dofs
     pp = PartitionedProblem(m, rank, world, local_rank, material=(_lib.MAT_LINEAR_ELASTIC, (210e9, 0.3)), fixed_dofs=fixed_g,
-                            options={"patch_elems": args.patch} if args.patch else None)
+                            options=dict([("patch_elems", args.patch)] if args.patch else [], **{k: float(v) for k, v in (o.split("=") for o in args.opt)}) or None)
     h = pp.handle
     n_local_dofs, n_own_dofs = 3 * pp.local_nodes.size, 3 * pp.n_owned
     h.set_stream(torch.cuda.current_stream().cuda_stream)

@@ -127,6 +127,8 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         else h->timing.release();
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
+    } else if (!strcmp(key, "async_gather")) {
+        h->async_gather = value != 0;
     } else if (!strcmp(key, "fused_halo")) {
         h->fused_halo = value != 0;
     } else if (!strcmp(key, "fused_interface")) {

@@ -20,6 +20,7 @@ struct jfem_handle {
     // options
     int patch_elems = 256;
     bool deterministic = true, affine = true, warp_specialised = true;
+    bool async_gather = true;           // option "async_gather": LDGSTS look-ahead gather in the ws kernel
     int debug_skip = 0;                 // profiling aid (option "debug_skip"): phases of the ws kernel to leave out
     int lane_window = 48;               // candidates examined per lane by the bank-aware lane assignment (0 = off)
     // material

@@ -35,6 +35,7 @@ struct PatchKArgs {
     const uint32_t *slot_node; // partial slot -> node id (only read by the non-deterministic atomic mode)
     long long elem_offset;
     int project, atomic_iface, nbuf;
+    int gmode;                 // ws kernel: 0 = look-ahead gather through registers (LDG + park), 1 = asynchronous copies (LDGSTS)
     int dbg;                   // debug_skip bits: 1 = no global stores in phase 2, 2 = no row loops, 4 = no phase 1, 8 = no look-ahead gather
     int *fail;
     const int *done;
@@ -470,10 +471,40 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 Xs[3 * j] = __ldg(g); Xs[3 * j + 1] = __ldg(g + 1); Xs[3 * j + 2] = __ldg(g + 2);
             }
         };
+        // alternative look-ahead gather (a.gmode = 1): asynchronous copies (LDGSTS) straight into the other tiles -- no
+        // registers, no parking pass; ghost values (rare) are read synchronously from the landing buffer
+        auto gather_async = [&](const unsigned char *pa, double *xs, double *Xs) {
+            const int *hdr = reinterpret_cast<const int *>(pa);
+            const int np = hdr[0], nx = a.x_all ? np : hdr[1];
+            if (!halo_seen && (hdr[3] & 0x10000)) {
+                if (tid < a.hf.n_nb) {
+                    const volatile unsigned long long *f = a.hf.my_flag[tid];
+                    while (*f < a.hf.seq) { }
+                }
+                named_sync(3, WS_T);
+                __threadfence_system();
+                halo_seen = true;
+            }
+            const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
+            const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
+            for (int j = tid; j < np; j += T) {   // one node per lane and step (a flat item-per-lane mapping touches a third of
+                bool ghost;                       // the sectors but was measured slower: 2 500 instead of 1 450 issue cycles)
+                const double *g = node_ptr(pn[j], ghost);
+                double *d = xs + 3 * j;
+                if (ghost) { d[0] = __ldcv(g); d[1] = __ldcv(g + 1); d[2] = __ldcv(g + 2); }
+                else { cp_async8(d, g); cp_async8(d + 1, g + 1); cp_async8(d + 2, g + 2); }
+            }
+            for (int j = tid; j < nx; j += T) {
+                const double *g = a.coords + 3 * (long long)xl[j];
+                double *d = Xs + 3 * j;
+                cp_async8(d, g); cp_async8(d + 1, g + 1); cp_async8(d + 2, g + 2);
+            }
+            cp_async_commit();
+        };
         if (n_it > 0) {
             mbar_wait(&A_full[0], 0);
-            load_regs(sm + L.A);
-            store_regs(sm + L.A, xs0, Xs0);
+            if (a.gmode) { gather_async(sm + L.A, xs0, Xs0); cp_async_wait_all(); }
+            else { load_regs(sm + L.A); store_regs(sm + L.A, xs0, Xs0); }
             named_sync(2, WS_T);
         }
         for (int i = 0; i < n_it; i++) {
@@ -484,7 +515,8 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
             if (has_next) {
                 mbar_wait(&A_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
                 if (tm) a.timing[i * 8 + 5] = clock64();
-                load_regs(pan);
+                if (a.gmode) gather_async(pan, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
+                else load_regs(pan);
             }
             // part A of patch i and part B of patch i-1 are dead (barrier at the end of the previous iteration): refill
             if (tid == WS_T - 32) {
@@ -507,7 +539,8 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
             if (tm) a.timing[i * 8 + 3] = clock64();
             mbar_arrive(&stage_full[i & 1]);
             if (has_next) {
-                store_regs(pan, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
+                if (a.gmode) cp_async_wait_all();
+                else store_regs(pan, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
                 named_sync(2, WS_T);   // tile (i+1)&1 complete and visible to every compute warp
             }
             if (tm) a.timing[i * 8 + 4] = clock64();
@@ -857,7 +890,7 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         a.coords = h->coords.p; a.x = x; a.ulin = h->ulin.p; a.y = y; a.ipart = h->ipart.p; a.slot_node = h->slot_node.p;
         a.elem_offset = D.elem_offset;
         a.project = (flags & JFEM_PROJECT) ? 1 : 0; a.atomic_iface = atomic_iface;
-        a.fail = h->dflags.p; a.done = done; a.timing = h->timing.p; a.nbuf = 2; a.dbg = h->debug_skip;
+        a.fail = h->dflags.p; a.done = done; a.timing = h->timing.p; a.nbuf = 2; a.dbg = h->debug_skip; a.gmode = h->async_gather ? 1 : 0;
         int rc;
         switch (h->mesh.nnpe) {
             case 10: rc = dispatch_threads<10>(h, D, a, mode); break;

@@ -9,6 +9,7 @@ h = _lib.Handle(10, m.coords, m.conn); h.set_material(0, (210e9, 0.3))
 h.set_option("debug_timing", 1)
 import os
 h.set_option("debug_skip", int(os.environ.get("JFEM_SKIP", "0")))
+h.set_option("async_gather", int(os.environ.get("JFEM_ASYNC", "0")))
 print("debug_skip =", os.environ.get("JFEM_SKIP", "0"))
 x = torch.from_numpy(mesh.test_vector(m.n_dofs)).cuda(); y = torch.empty_like(x)
 h.set_stream(torch.cuda.current_stream().cuda_stream)
