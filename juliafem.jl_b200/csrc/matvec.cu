@@ -730,11 +730,11 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
     constexpr int NF = Pt::NF;
     auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     const size_t xtile = sizeof(double) * 3 * (size_t)(a.x_all ? D.max_nodes : D.max_nx);
-    if constexpr (MODE == OP_LINEAR && T == WS_T && NF == 1 && NNPE == 10 && CLS == CLASS_AFFINE) {
+    if constexpr (MODE == OP_LINEAR && T == WS_T && NF == 1 && (NNPE == 10 || NNPE == 8) && CLS == CLASS_AFFINE) {
         if (h->warp_specialised) {
             WsSmem L;
             if (ws_layout(D, a.x_all, L)) {
-                constexpr int GC = (CLS == CLASS_AFFINE && NNPE == 10) ? 1 : WS_GN;
+                constexpr int GC = (CLS == CLASS_AFFINE && NNPE == 10) ? 1 : WS_GN;   // only the register-path gather (async_gather = 0) uses it
                 auto kws = patch_kernel_ws<NNPE, CLS, MODE, Pt, GC>;
                 static int configured_ws = 0;
                 if (L.total > configured_ws) {
@@ -843,7 +843,7 @@ static int dispatch_threads(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, 
 // true when op_apply will run exactly one warp-specialised patch kernel (which can carry the halo exchange)
 bool ws_halo_capable(jfem_handle *h) {
     if (ensure_built(h) != JFEM_OK) return false;
-    if (h->mesh.nnpe != 10 || h->mat_kind != JFEM_MAT_LINEAR_ELASTIC || !h->warp_specialised || h->patch_elems != WS_T) return false;
+    if ((h->mesh.nnpe != 10 && h->mesh.nnpe != 8) || h->mat_kind != JFEM_MAT_LINEAR_ELASTIC || !h->warp_specialised || h->patch_elems != WS_T) return false;
     const PatchSetDev &D = h->dsets[CLASS_AFFINE];
     if (h->dsets[CLASS_GENERAL].n_elems != 0 || D.n_elems == 0) return false;
     WsSmem L;

@@ -12,7 +12,7 @@ struct PField {
     const uint32_t *w;
     JF_HD double operator()(int k, int c) const { return base[3 * (w[k] & 0xFFFFu) + c]; }
 };
-struct XField4 {   // coordinates of the 4 vertices of an affine Tet10: slots packed two per word
+struct XField4 {   // coordinates of the 4 geometry nodes of an affine element (Tet10 vertices; Hex8 nodes 0, 1, 3, 4): slots packed two per word
     const double *base;
     const uint32_t *xw;
     JF_HD double operator()(int k, int c) const { return base[3 * ((k & 1) ? (xw[k >> 1] >> 16) : (xw[k >> 1] & 0xFFFFu)) + c]; }
@@ -37,6 +37,15 @@ JF_HD bool element_phase(const Pt &pt, long long el, const uint32_t *et, int tid
         Pt q = pt;
         q.load(el);
         tet10_affine_linear(q.la, q.mu, U, X, out);
+        return true;
+    } else if constexpr (CLS == CLASS_AFFINE && MODE == OP_LINEAR && NNPE == 8) {
+        uint32_t xw[2];
+        xw[0] = et[NNPE * T + tid]; xw[1] = et[(NNPE + 1) * T + tid];
+        PField U{xs, w};
+        XField4 X{Xs, xw};
+        Pt q = pt;
+        q.load(el);
+        hex8_affine_linear(q.la, q.mu, U, X, out);
         return true;
     } else {
         PField X{Xs, w};

@@ -64,6 +64,26 @@ void classify_elements(MeshHost &m, bool use_affine) {
     m.cls.assign(m.n_elems, CLASS_GENERAL);
     if (!use_affine) return;
     if (m.nnpe == 4) { std::fill(m.cls.begin(), m.cls.end(), (uint8_t)CLASS_AFFINE); return; }
+    if (m.nnpe == 8) {   // Hex8 is affine when it is a parallelepiped: x_k = x_0 + (edge vectors of node 0) for every node
+        static const int EU[8] = {0, 1, 1, 0, 0, 1, 1, 0}, EV[8] = {0, 0, 1, 1, 0, 0, 1, 1}, EW[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < m.n_elems; e++) {
+            const int32_t *c = &m.conn[e * 8];
+            const double *x0 = &m.coords[3 * (int64_t)c[0]], *x1 = &m.coords[3 * (int64_t)c[1]], *x3 = &m.coords[3 * (int64_t)c[3]],
+                         *x4 = &m.coords[3 * (int64_t)c[4]];
+            double h2 = 0;
+            for (int d = 0; d < 3; d++) h2 += (x1[d] - x0[d]) * (x1[d] - x0[d]) + (x3[d] - x0[d]) * (x3[d] - x0[d]) + (x4[d] - x0[d]) * (x4[d] - x0[d]);
+            bool ok = true;
+            for (int k = 0; k < 8 && ok; k++)
+                for (int d = 0; d < 3; d++) {
+                    const double want = x0[d] + EU[k] * (x1[d] - x0[d]) + EV[k] * (x3[d] - x0[d]) + EW[k] * (x4[d] - x0[d]);
+                    const double dv = m.coords[3 * (int64_t)c[k] + d] - want;
+                    if (dv * dv > 1e-28 * h2) { ok = false; break; }
+                }
+            m.cls[e] = ok ? CLASS_AFFINE : CLASS_GENERAL;
+        }
+        return;
+    }
     if (m.nnpe != 10) return;
     static const int EA[6] = {0, 1, 0, 0, 1, 2}, EB[6] = {1, 2, 2, 3, 3, 3};
 #pragma omp parallel for schedule(static)
@@ -181,7 +201,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
         PatchSetHost &S = sets[c];
         S = PatchSetHost();
         S.cls = c; S.nnpe = nnpe; S.EP = EP;
-        S.nxr = (c == CLASS_AFFINE && nnpe == 10) ? 2 : 0;
+        S.nxr = (c == CLASS_AFFINE && (nnpe == 10 || nnpe == 8)) ? 2 : 0;
         for (int64_t e = 0; e < m.n_elems; e++) if (m.cls[e] == c) S.elem_perm.push_back(e);
         S.n_elems = (int64_t)S.elem_perm.size();
         if (S.n_elems == 0) continue;
@@ -266,6 +286,10 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
         PatchSetHost &S = sets[c];
         if (S.n_elems == 0) continue;
         const int nvx = S.nxr ? 4 : 0;
+        // element nodes whose coordinates an affine element needs: Tet10 vertices; Hex8 node 0 and its three edge neighbours
+        static const int XN10[4] = {0, 1, 2, 3}, XN8[4] = {0, 1, 3, 4};
+        const int *xn = nnpe == 8 ? XN8 : XN10;
+        auto xidx = [&](int k) { for (int v = 0; v < nvx; v++) if (xn[v] == k) return v; return -1; };
         // sizes needed for the layout: max_nx, max_rows
         std::vector<int> nxs(S.n_patches, 0), nrw(S.n_patches, 0);
 #pragma omp parallel for schedule(dynamic, 64)
@@ -278,7 +302,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                 for (int k = 0; k < nnpe; k++) {
                     int j = (int)(std::lower_bound(ids.begin(), ids.end(), m.conn[S.elem_perm[i] * nnpe + k]) - ids.begin());
                     cnt[j]++;
-                    if (k < nvx) nx[j] = 1;
+                    if (xidx(k) >= 0) nx[j] = 1;
                 }
             nrw[p] = *std::max_element(cnt.begin(), cnt.end());
             nxs[p] = (int)std::count(nx.begin(), nx.end(), (uint8_t)1);
@@ -314,7 +338,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                     int j = local_of(m.conn[S.elem_perm[lo + i] * nnpe + k]);
                     loc[(size_t)i * nnpe + k] = (uint16_t)j;
                     cnt[j]++;
-                    if (k < nvx) xslot[j] = 0;
+                    if (xidx(k) >= 0) xslot[j] = 0;
                 }
             int nx = 0;
             for (int j = 0; j < np; j++) if (xslot[j] == 0) xslot[j] = nx++;
@@ -344,7 +368,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                         const int e = joff[fill[j]++] + qpos[j];
                         ent[(size_t)i * nnpe + k] = (uint16_t)e;
                         lo_.idx[(size_t)i * lo_.ns + k] = (uint16_t)j;
-                        if (k < nvx) lo_.idx[(size_t)i * lo_.ns + nnpe + k] = (uint16_t)xslot[j];
+                        if (xidx(k) >= 0) lo_.idx[(size_t)i * lo_.ns + nnpe + xidx(k)] = (uint16_t)xslot[j];
                         lo_.idx[(size_t)i * lo_.ns + nnpe + nvx + k] = (uint16_t)e;
                     }
             }
@@ -450,9 +474,9 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
             for (int t = 0; t < ne; t++) {
                 const int i = perm[t];
                 for (int k = 0; k < nnpe; k++) bet[(size_t)k * EP + t] = (uint32_t)loc[(size_t)i * nnpe + k] | ((uint32_t)ent[(size_t)i * nnpe + k] << 16);
-                for (int k = 0; k < nvx; k += 2)
-                    bet[(size_t)(nnpe + k / 2) * EP + t] =
-                        (uint32_t)xslot[loc[(size_t)i * nnpe + k]] | ((uint32_t)xslot[loc[(size_t)i * nnpe + k + 1]] << 16);
+                for (int v = 0; v < nvx; v += 2)
+                    bet[(size_t)(nnpe + v / 2) * EP + t] =
+                        (uint32_t)xslot[loc[(size_t)i * nnpe + xn[v]]] | ((uint32_t)xslot[loc[(size_t)i * nnpe + xn[v + 1]]] << 16);
             }
             for (int q = 0; q < np; q++) {
                 const int j = order[q];

@@ -101,7 +101,7 @@ extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, 
 #define RUN(N, C, TT) run_set<N, C, TT>(S, off, m, pt, x, y, project, ipart)
 #define RUN_T(N, C) do { if (EP == 128) RUN(N, C, 128); else if (EP == 256) RUN(N, C, 256); else RUN(N, C, 512); } while (0)
         if (nnpe == 10) { if (c == CLASS_AFFINE) RUN_T(10, CLASS_AFFINE); else RUN_T(10, CLASS_GENERAL); }
-        else if (nnpe == 8) RUN_T(8, CLASS_GENERAL);
+        else if (nnpe == 8) { if (c == CLASS_AFFINE) RUN_T(8, CLASS_AFFINE); else RUN_T(8, CLASS_GENERAL); }
         else RUN_T(4, CLASS_AFFINE);
         off += S.n_elems;
     }

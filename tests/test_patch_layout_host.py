@@ -76,7 +76,19 @@ def test_tet10_curved_general(hostcheck, oracle, jf):
 def test_hex8_and_tet4(hostcheck, oracle, jf):
     m = distorted_hex8(jf.mesh, n=9)
     u = jf.mesh.test_vector(m.n_dofs)
-    y, _ = run(hostcheck, m, u, EP=128)
+    y, st = run(hostcheck, m, u, EP=128)
+    assert st[7] == 0                                         # distorted: no parallelepipeds
+    assert relerr(y, oracle.matfree(8, m.coords, m.conn, u, par=(210e9, 0.3))) < 1e-12
+    # parallelepiped elements (lattice sheared and stretched by an affine map) take the closed form; half of the mesh distorted
+    m = jf.mesh.hex8_lattice(9, 7, 8, 0.25)
+    A = np.array([[1.0, 0.3, 0.1], [0.0, 0.8, 0.2], [0.05, 0.0, 1.3]])
+    m.coords = m.coords @ A.T
+    rng = np.random.default_rng(1)
+    sel = m.coords[:, 2] > 1.2
+    m.coords[sel] += 0.01 * rng.standard_normal((int(sel.sum()), 3))
+    u = jf.mesh.test_vector(m.n_dofs)
+    y, st = run(hostcheck, m, u, EP=128)
+    assert 0 < st[7] < m.n_elems
     assert relerr(y, oracle.matfree(8, m.coords, m.conn, u, par=(210e9, 0.3))) < 1e-12
     m = jf.mesh.tet4_kuhn(5, 4, 3, 1.0)
     u = jf.mesh.test_vector(m.n_dofs)
