@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (jfem_set_option), repeatable")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1, help="1: replay the timed loop as one CUDA graph (no host launch jitter between "
+                    "ranks); 0: launch every step from the host; default: graph for N > 1")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
     ap.add_argument("--cg", action="store_true", help="also time a full CG solve (||r|| <= 1e-8 ||b||) on the workload")
     args = ap.parse_args()
@@ -210,19 +212,48 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        if flush is not None:
-            flush.fill_(float(k))
-        ev[k][0].record()
-        step()
-        ev[k][1].record()
-    barrier()
+    use_graph = True if args.graph < 0 else bool(args.graph)
+
+    def timed_loop(ev):
+        for k in range(args.steps):
+            if flush is not None:
+                flush.fill_(float(k))
+            ev[k][0].record()
+            step()
+            ev[k][1].record()
+
+    host_s = None
+    if use_graph:
+        # The K timed steps (L2 flush, event, K.u, event) are captured once and replayed as ONE graph launch: every rank's
+        # GPU then runs its K steps back to back with no host in the loop, so a late host launch on one rank cannot stall
+        # its neighbours at the halo gate.  Same kernels, same events, same barrier + synchronize bracket.
+        ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(args.steps)]
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream()
+        torch.cuda.synchronize()
+        h.set_stream(cap.cuda_stream)          # (synchronises the old stream: must happen outside the capture)
+        with torch.cuda.graph(g, stream=cap):
+            timed_loop(ev)
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        barrier()
+        g.replay()
+        barrier()
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t0 = time.perf_counter()
+        timed_loop(ev)
+        host_s = (time.perf_counter() - t0) / args.steps
+        barrier()
     launches_timed = int(h.info().total_launches) - launches_before     # kernels of the library launched inside the timed region
     times = np.array([a.elapsed_time(b) for a, b in ev])       # ms, device time of each step
     ms = float(times.mean())
+    per_rank = None
     if world > 1:
+        st = torch.tensor([ms, float(times.min()), float(np.median(times)), float(times.max())], device=dev, dtype=torch.float64)
+        allst = [torch.zeros_like(st) for _ in range(world)]
+        dist.all_gather(allst, st)
+        per_rank = [[round(float(v), 5) for v in a.cpu()] for a in allst]      # mean, min, median, max of every rank (ms)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -282,7 +313,10 @@ def main():
                        "partition": ("z-slabs by contiguous node range, owner-computes + ghost elements; halo via "
                                      + ("ncclSend/ncclRecv" if args.nccl_halo else "peer-memory stores over NVLink (CUDA IPC) issued from inside the patch kernel; "
                                         "patches that read ghost values run last and wait for the neighbours' flags")) if world > 1 else "single GPU",
-                       "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds)},
+                       "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds),
+                       "launch": "one CUDA graph replay of the K timed steps" if use_graph else "per-step host launches",
+                       "host_enqueue_ms_per_step": None if host_s is None else host_s * 1e3,
+                       "per_rank_ms_mean_min_median_max": per_rank, "rank0_first_steps_ms": [round(float(v), 4) for v in times[:16]]},
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
                     "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},
             "gpu_launches": launches_timed,

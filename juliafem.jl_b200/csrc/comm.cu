@@ -99,9 +99,9 @@ __global__ void halo_push_kernel(P2PArgs a, const int32_t *__restrict__ nodes, c
         while (q >= a.send_off[nb + 1]) nb++;
         a.peer_land[nb][i - 3 * a.send_off[nb]] = x[3LL * nodes[q] + (i - 3 * q)];
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();   // one system fence per block (cumulative over the barrier), not one per warp
         const unsigned int t = atomicAdd(ticket, 1u);
         if (t == gridDim.x - 1) {            // last block: all remote stores of this rank are fenced -> publish
             *ticket = 0;
@@ -116,9 +116,9 @@ __global__ void halo_pull_kernel(P2PArgs a, const double *__restrict__ land, con
     if (threadIdx.x < a.n_nb) {
         const volatile unsigned long long *f = a.my_flag[threadIdx.x];
         while (*f < seq) { }
+        __threadfence_system();
     }
     __syncthreads();
-    __threadfence_system();
     const long long n3 = 3 * a.recv_off[a.n_nb];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
         const long long q = i / 3;

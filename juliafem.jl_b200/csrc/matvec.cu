@@ -426,9 +426,9 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 if (tid < a.hf.n_nb) {
                     const volatile unsigned long long *f = a.hf.my_flag[tid];
                     while (*f < a.hf.seq) { }
+                    __threadfence_system();   // acquire side: only the polling threads fence; the barrier extends it to the block
                 }
                 named_sync(3, WS_T);
-                __threadfence_system();
                 halo_seen = true;
             }
             const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
@@ -480,9 +480,9 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 if (tid < a.hf.n_nb) {
                     const volatile unsigned long long *f = a.hf.my_flag[tid];
                     while (*f < a.hf.seq) { }
+                    __threadfence_system();   // acquire side: only the polling threads fence; the barrier extends it to the block
                 }
                 named_sync(3, WS_T);
-                __threadfence_system();
                 halo_seen = true;
             }
             const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
@@ -559,9 +559,12 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 while (q >= a.hf.send_off[nb + 1]) nb++;
                 a.hf.peer_land[nb][i - 3 * a.hf.send_off[nb]] = a.x[3LL * a.hf.send_nodes[q] + (i - 3 * q)];
             }
-            __threadfence_system();
+            // one system-scope fence per block, by the thread that takes the ticket (the barrier orders the other threads'
+            // remote stores before it; fence cumulativity makes them visible before the flag).  A fence in every thread
+            // costs one MEMBAR.SYS per warp, and its latency grows with the number of mapped peers (8 GPUs: +40 us per step).
             named_sync(1, WS_H);
             if (hid == 0) {
+                __threadfence_system();
                 const unsigned int t = atomicAdd(a.hf.ticket, 1u);
                 if (t == gridDim.x - 1) {
                     *a.hf.ticket = 0;
