@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (jfem_set_option), repeatable")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--spinup", type=float, default=0.4, help="seconds of untimed load before the warm-up steps (clock ramp)")
     ap.add_argument("--graph", type=int, default=-1, help="1: replay the timed loop as one CUDA graph (no host launch jitter between "
                     "ranks); 0: launch every step from the host; default: graph for N > 1")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
@@ -203,15 +204,21 @@ def main():
     def step():
         h.matvec(x, y, flags=_lib.PROJECT)
 
+    # untimed spin-up: a GPU that has been idle (setup is host work) needs tens of ms under load to reach its boost clock;
+    # with W warm-up steps of ~50 us each a rank could still be ramping during the timed region and stall its neighbours
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < args.spinup:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
     barrier()
     info = h.info()
     launches_before = int(info.total_launches)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank)       # every rank watches its own GPU
+    sampler.start()
     use_graph = True if args.graph < 0 else bool(args.graph)
 
     def timed_loop(ev):
@@ -228,17 +235,34 @@ def main():
         # GPU then runs its K steps back to back with no host in the loop, so a late host launch on one rank cannot stall
         # its neighbours at the halo gate.  Same kernels, same events, same barrier + synchronize bracket.
         ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(args.steps)]
-        g = torch.cuda.CUDAGraph()
-        cap = torch.cuda.Stream()
+        ok = 1.0
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream()
+            torch.cuda.synchronize()
+            h.set_stream(cap.cuda_stream)          # (synchronises the old stream: must happen outside the capture)
+            with torch.cuda.graph(g, stream=cap):
+                timed_loop(ev)
+        except Exception as exc:                   # capture unsupported here: fall back to per-step host launches
+            ok = 0.0
+            print(f"[bench] CUDA graph capture failed ({str(exc)[:120]}); timing with per-step launches", file=sys.stderr, flush=True)
         torch.cuda.synchronize()
-        h.set_stream(cap.cuda_stream)          # (synchronises the old stream: must happen outside the capture)
-        with torch.cuda.graph(g, stream=cap):
-            timed_loop(ev)
         h.set_stream(torch.cuda.current_stream().cuda_stream)
-        barrier()
-        g.replay()
-        barrier()
-    else:
+        if world > 1:                              # every rank must take the same path
+            t = torch.tensor([ok], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = float(t.item())
+        if ok:
+            barrier()
+            g.replay()
+            barrier()
+        else:
+            use_graph = False
+            if world > 1:                          # ranks may have enqueued different numbers of exchanges: re-synchronise the halo sequence
+                t = torch.tensor([float(h.comm_p2p_seq())], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                h.comm_p2p_seq(int(t.item()) + 2)
+    if not use_graph:
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         t0 = time.perf_counter()
@@ -257,7 +281,17 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        mine = torch.tensor([clocks["sm_mhz"] or 0.0, float(len(clocks["reasons"]))], device=dev, dtype=torch.float64)
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, clocks["reasons"])
+        clocks["per_rank_sm_mhz"] = [float(c[0]) for c in allc]
+        vals = [v for v in clocks["per_rank_sm_mhz"] if v > 0]
+        clocks["sm_mhz"] = min(vals) if vals else None        # the slowest GPU's median clock under load
+        clocks["reasons"] = sorted({r for g in gathered for r in (g or [])})
 
     # end to end through the C ABI with pinned host buffers (H2D of x, D2H of y inside the timed region)
     xh = torch.empty(n_local_dofs, dtype=torch.float64, pin_memory=True)

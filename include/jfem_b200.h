@@ -152,6 +152,11 @@ int jfem_comm_set_halo(jfem_handle *h, int n_neighbours, const int32_t *neighbou
  * (3*total_recv_nodes+8). */
 int jfem_comm_p2p_export(jfem_handle *h, char *handles128);
 int jfem_comm_p2p_import(jfem_handle *h, const char *all_handles, const int64_t *recv_offsets, const int64_t *halves);
+/* Halo sequence number of the peer-memory exchange (it must agree on all ranks; every exchange advances it by one).
+ * *seq returns the current value; set_to >= 0 sets it first.  Only needed to re-synchronise ranks after some of them
+ * abandoned enqueued work (e.g. a failed CUDA-graph capture); no counterpart in the reference (its MPI halo is stateless,
+ * benchmarks/multigpu_mpi_benchmark.jl:302-360). */
+int jfem_comm_p2p_seq(jfem_handle *h, int64_t set_to, int64_t *seq);
 int jfem_comm_destroy(jfem_handle *h);
 
 #ifdef __cplusplus

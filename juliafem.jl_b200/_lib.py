@@ -25,7 +25,7 @@ EXPORTS = [
     "jfem_internal_force", "jfem_set_linearization", "jfem_commit_state", "jfem_get_state", "jfem_set_state",
     "jfem_element_matrices", "jfem_csr_size", "jfem_csr_pattern", "jfem_assemble_csr", "jfem_spmv", "jfem_cg",
     "jfem_newton_krylov", "jfem_comm_unique_id", "jfem_comm_init", "jfem_comm_set_halo", "jfem_comm_p2p_export",
-    "jfem_comm_p2p_import", "jfem_comm_destroy",
+    "jfem_comm_p2p_import", "jfem_comm_p2p_seq", "jfem_comm_destroy",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.jfem_comm_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
         L.jfem_comm_p2p_export.argtypes = [vp, C.c_char_p]
         L.jfem_comm_p2p_import.argtypes = [vp, C.c_char_p, vp, vp]
+        L.jfem_comm_p2p_seq.argtypes = [vp, i64, C.POINTER(i64)]
         L.jfem_comm_destroy.argtypes = [vp]
         for name in EXPORTS:
             if name != "jfem_last_error":
@@ -315,6 +316,12 @@ class Handle:
         buf = C.create_string_buffer(128)
         check(lib().jfem_comm_p2p_export(self._h, buf))
         return buf.raw
+
+    def comm_p2p_seq(self, set_to: int = -1) -> int:
+        """Halo sequence number (must agree on all ranks); set_to >= 0 sets it first."""
+        out = C.c_int64(0)
+        check(lib().jfem_comm_p2p_seq(self._h, set_to, C.byref(out)))
+        return int(out.value)
 
     def comm_p2p_import(self, all_handles: bytes, recv_offsets, halves):
         ro = np.ascontiguousarray(recv_offsets, dtype=np.int64)

@@ -343,6 +343,13 @@ extern "C" int jfem_comm_set_halo(jfem_handle *h, int nnb, const int32_t *nb_ran
     return JFEM_OK;
 }
 
+extern "C" int jfem_comm_p2p_seq(jfem_handle *h, int64_t set_to, int64_t *seq) {
+    if (!h) { jfem_set_error("null handle"); return JFEM_EINVAL; }
+    if (set_to >= 0) { h->p2p_seq = (unsigned long long)set_to; h->halo_armed = false; }
+    if (seq) *seq = (int64_t)h->p2p_seq;
+    return JFEM_OK;
+}
+
 extern "C" int jfem_comm_destroy(jfem_handle *h) {
     if (h && h->comm) { N.destroy(h->comm); h->comm = nullptr; h->n_ranks = 1; }
     return JFEM_OK;
