@@ -1,5 +1,7 @@
 // handle.h -- the opaque jfem_handle and the internal entry points shared by the .cu files.
 #pragma once
+#include <unordered_map>
+
 #include "common.h"
 
 struct ncclComm;
@@ -95,6 +97,7 @@ struct jfem_handle {
     bool halo_in_kernel = false;        // the last exchange ran inside the patch kernel (statistics)
     std::vector<int64_t> p2p_peer_off;
     std::vector<size_t> p2p_peer_half;
+    std::unordered_map<const void *, size_t> smem_attr;   // kernels already opted into this much dynamic shared memory (on this device)
     // stats
     int64_t matvec_launches = 0, total_launches = 0, last_smem = 0, last_blocks_per_sm = 0;
 

@@ -713,6 +713,17 @@ int ensure_built(jfem_handle *h) {
 
 // ------------------------------------------------------------------------------------------------ launch
 
+// Opt a kernel into `bytes` of dynamic shared memory.  The attribute is per device, so the cache lives in the handle
+// (one handle = one device), not in a function-local static.
+static int ensure_dynamic_smem(jfem_handle *h, const void *func, size_t bytes) {
+    size_t &have = h->smem_attr[func];
+    if (bytes > have) {
+        JFEM_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return JFEM_OK;
+}
+
 static bool ws_layout(const PatchSetDev &D, int x_all, WsSmem &L) {
     auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
     const size_t xtile = sizeof(double) * 3 * (size_t)(x_all ? D.max_nodes : D.max_nx);
@@ -739,11 +750,7 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
             if (ws_layout(D, a.x_all, L)) {
                 constexpr int GC = (CLS == CLASS_AFFINE && NNPE == 10) ? 1 : WS_GN;   // only the register-path gather (async_gather = 0) uses it
                 auto kws = patch_kernel_ws<NNPE, CLS, MODE, Pt, GC>;
-                static int configured_ws = 0;
-                if (L.total > configured_ws) {
-                    JFEM_CUDA(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-                    configured_ws = L.total;
-                }
+                JFEM_TRY(ensure_dynamic_smem(h, (const void *)kws, (size_t)L.total));
                 h->last_smem = L.total; h->last_blocks_per_sm = 1;
                 int grid = h->n_sms < D.n_patches ? h->n_sms : D.n_patches;
                 if (a.tail) {
@@ -768,11 +775,7 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
     if (smem > 227 * 1024) { a.nbuf = 1; smem = r128(16 + (size_t)D.L.stride + tiles); }
     if (smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
     auto kern = patch_kernel<NNPE, CLS, MODE, Pt, T>;
-    static size_t configured = 0;
-    if (smem > configured) {
-        JFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    JFEM_TRY(ensure_dynamic_smem(h, (const void *)kern, smem));
     int per_sm = 1;
     JFEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
     if (per_sm < 1) per_sm = 1;

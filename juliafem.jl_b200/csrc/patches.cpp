@@ -114,7 +114,7 @@ namespace {
 struct LaneOpt {
     int ns = 0, ns_assign = 0;        // slots per element; leading slots the lane assignment looks at
     std::vector<uint16_t> idx;        // [elem][slot]
-    int model(const std::vector<int> &perm, int ne, long long *per_slot = nullptr) const {   // modelled wavefronts (per component) of one patch
+    int model(const std::vector<int> &perm, int ne) const {   // modelled wavefronts (per component) of one patch
         int total = 0;
         for (int h0 = 0; h0 < ne; h0 += 16) {
             int h1 = std::min(h0 + 16, ne);
@@ -129,7 +129,6 @@ struct LaneOpt {
                     if (k == nseen[b]) { seen[b][nseen[b]++] = v; mx = std::max(mx, nseen[b]); }
                 }
                 total += mx;
-                if (per_slot) per_slot[s] += mx;
             }
         }
         return total;
@@ -374,9 +373,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
             }
             std::vector<int> perm(ne);
             std::iota(perm.begin(), perm.end(), 0);
-            static long long dbg0[64], dbg1[64];
-            const bool dbg = getenv("JFEM_WF_DEBUG") != nullptr;
-            wf0 += lo_.model(perm, ne, dbg ? dbg0 : nullptr);
+            wf0 += lo_.model(perm, ne);
             if (lane_window > 0) {
                 lo_.assign(perm, ne, lane_window);
                 // Staging rows: a node's contributions may take its rows in any order (the order only fixes the summation
@@ -449,13 +446,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                     }
                 }
             }
-            wf1 += lo_.model(perm, ne, dbg ? dbg1 : nullptr);
-            if (dbg && p == S.n_patches - 1) {
-                for (int k = 0; k < lo_.ns; k++) fprintf(stderr, "%.2f ", dbg0[k] / (16.0 * S.n_patches));
-                fprintf(stderr, "\n");
-                for (int k = 0; k < lo_.ns; k++) fprintf(stderr, "%.2f ", dbg1[k] / (16.0 * S.n_patches));
-                fprintf(stderr, "\n");
-            }
+            wf1 += lo_.model(perm, ne);
             wfi += lo_.ns * ((ne + 15) / 16);
             for (int t = 0; t < ne; t++) new_perm[lo + t] = S.elem_perm[lo + perm[t]];
             // ---- write the blob
