@@ -73,6 +73,10 @@ function create_handle(elements::Vector, device::Integer)
     return h[], node_ids, remap
 end
 
+"Tuning knobs of the library (include/jfem_b200.h: \"patch_elems\", \"deterministic\", \"affine_fast_path\", \"warp_specialised\", ...)."
+set_option!(data::ElasticityDataB200, key::AbstractString, value::Real) =
+    check(ccall((:jfem_set_option, libjfem), Cint, (Ptr{Cvoid}, Cstring, Cdouble), data.handle, key, Float64(value)))
+
 function initialize_backend(backend::GPU, physics::Physics, time::Float64)
     handle, node_ids, remap = create_handle(physics.body_elements, 0)
     data = ElasticityDataB200(handle, node_ids, 3 * length(node_ids))
