@@ -206,11 +206,19 @@ def main():
 
     # untimed spin-up: a GPU that has been idle (setup is host work) needs tens of ms under load to reach its boost clock;
     # with W warm-up steps of ~50 us each a rank could still be ramping during the timed region and stall its neighbours
+    # (the number of spin-up steps must be the same on every rank: each step is a halo exchange with the neighbours)
+    torch.cuda.synchronize()
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < args.spinup:
-        for _ in range(50):
-            step()
-        torch.cuda.synchronize()
+    for _ in range(10):
+        step()
+    torch.cuda.synchronize()
+    t_step = torch.tensor([(time.perf_counter() - t_spin) / 10], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
+    n_spin = int(min(20000, max(0, args.spinup / max(float(t_step.item()), 1e-6))))
+    for _ in range(n_spin):
+        step()
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step()
     barrier()
