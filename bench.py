@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spinup", type=float, default=0.4, help="seconds of untimed load before the warm-up steps (clock ramp)")
     ap.add_argument("--graph", type=int, default=-1, help="1: replay the timed loop as one CUDA graph (no host launch jitter between "
-                    "ranks); 0: launch every step from the host; default: graph for N > 1")
+                    "ranks); 0: launch every step from the host; default: 1")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
     ap.add_argument("--cg", action="store_true", help="also time a full CG solve (||r|| <= 1e-8 ||b||) on the workload")
     args = ap.parse_args()
@@ -207,6 +207,7 @@ def main():
     # untimed spin-up: a GPU that has been idle (setup is host work) needs tens of ms under load to reach its boost clock;
     # with W warm-up steps of ~50 us each a rank could still be ramping during the timed region and stall its neighbours
     # (the number of spin-up steps must be the same on every rank: each step is a halo exchange with the neighbours)
+    step()                                   # first call builds the patches (host work): keep it out of the step-time estimate
     torch.cuda.synchronize()
     t_spin = time.perf_counter()
     for _ in range(10):
