@@ -21,7 +21,7 @@ using namespace jf;
 
 template <int NNPE, int CLS, int T>
 static void run_set(const PatchSetHost &S, long long elem_offset, const MeshHost &m, const PtLinear &pt, const double *x, double *y, int project,
-                    std::vector<double> &ipart) {
+                    std::vector<double> &ipart, long long n_owned, const double *land) {
     const PatchLayout &L = S.L;
     const bool x_all = S.nxr == 0;
     std::vector<double> xs(3 * (size_t)S.max_nodes), Xs(3 * (size_t)(x_all ? S.max_nodes : S.max_nx)), stage(3 * (size_t)S.max_entries);
@@ -34,14 +34,19 @@ static void run_set(const PatchSetHost &S, long long elem_offset, const MeshHost
         const uint32_t *qn = reinterpret_cast<const uint32_t *>(b + L.off_qn);
         const uint8_t *ql = b + L.off_ql;
         const uint16_t *jo = reinterpret_cast<const uint16_t *>(b + L.off_jo);
+        bool seen_ghost = false;
         for (int j = 0; j < np; j++)
             for (int c = 0; c < 3; c++) {
-                xs[3 * j + c] = x[3 * (size_t)pn[j] + c];
+                // fused halo (matvec.cu node_ptr): ghost nodes (id >= n_owned) are read from the landing buffer, in ghost order
+                const bool ghost = n_owned >= 0 && (long long)pn[j] >= n_owned;
+                seen_ghost |= ghost;
+                xs[3 * j + c] = ghost ? land[3 * ((size_t)pn[j] - (size_t)n_owned) + c] : x[3 * (size_t)pn[j] + c];
                 if (x_all) Xs[3 * j + c] = m.coords[3 * (size_t)pn[j] + c];
             }
         if (!x_all)
             for (int j = 0; j < nx; j++)
                 for (int c = 0; c < 3; c++) Xs[3 * j + c] = m.coords[3 * (size_t)xl[j] + c];
+        if (seen_ghost != ((hdr[3] & 0x10000) != 0)) { jfem_set_error("ghost flag of patch %d wrong", p); throw 1; }
         std::fill(stage.begin(), stage.end(), 1e300);   // poison: every entry read must have been written
         for (int t = 0; t < ne; t++)
             element_phase<NNPE, CLS, OP_LINEAR, PtLinear, T>(pt, elem_offset + (long long)p * T + t, et, t, xs.data(), Xs.data(), nullptr, stage.data());
@@ -93,16 +98,32 @@ extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, 
     pt.la = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)); pt.mu = E / (2.0 * (1.0 + nu)); pt.sy = 0; pt.H = 0; pt.pe = nullptr; pt.pe_n = 0;
     for (long long i = 0; i < 3 * n_nodes; i++) y[i] = 1e300;   // poison: every dof must be written
     for (uint32_t n : hif.orphans) y[3 * (size_t)n] = y[3 * (size_t)n + 1] = y[3 * (size_t)n + 2] = 0.0;
+    // partitioned replay: ghost entries of x are poisoned, their values live in the landing buffer only
+    std::vector<double> xcopy(x, x + 3 * n_nodes), land(8, 0.0);
+    if (n_owned >= 0 && n_owned < n_nodes) {
+        land.assign(x + 3 * n_owned, x + 3 * n_nodes);
+        for (long long i = 3 * n_owned; i < 3 * n_nodes; i++) xcopy[i] = 1e300;
+    }
+    const double *xin = xcopy.data();
+    // ghost-reading patches must come after the others (the partial patch may stay last)
+    for (int c = 0; c < N_CLASSES; c++) {
+        const PatchSetHost &S = sets[c];
+        const int nfull = (int)(S.n_elems / EP);
+        for (int p = 1; p < nfull; p++)
+            if (S.ghosty[p] < S.ghosty[p - 1]) { jfem_set_error("ghost-reading patches are not ordered last"); return 2; }
+    }
     std::vector<double> ipart(3 * (size_t)hif.n_partials + 3, 1e300);
     long long off = 0;
     for (int c = 0; c < N_CLASSES; c++) {
         const PatchSetHost &S = sets[c];
         if (S.n_elems == 0) continue;
-#define RUN(N, C, TT) run_set<N, C, TT>(S, off, m, pt, x, y, project, ipart)
+#define RUN(N, C, TT) run_set<N, C, TT>(S, off, m, pt, xin, y, project, ipart, n_owned, land.data())
 #define RUN_T(N, C) do { if (EP == 128) RUN(N, C, 128); else if (EP == 256) RUN(N, C, 256); else RUN(N, C, 512); } while (0)
-        if (nnpe == 10) { if (c == CLASS_AFFINE) RUN_T(10, CLASS_AFFINE); else RUN_T(10, CLASS_GENERAL); }
-        else if (nnpe == 8) { if (c == CLASS_AFFINE) RUN_T(8, CLASS_AFFINE); else RUN_T(8, CLASS_GENERAL); }
-        else RUN_T(4, CLASS_AFFINE);
+        try {
+            if (nnpe == 10) { if (c == CLASS_AFFINE) RUN_T(10, CLASS_AFFINE); else RUN_T(10, CLASS_GENERAL); }
+            else if (nnpe == 8) { if (c == CLASS_AFFINE) RUN_T(8, CLASS_AFFINE); else RUN_T(8, CLASS_GENERAL); }
+            else RUN_T(4, CLASS_AFFINE);
+        } catch (int) { return 3; }
         off += S.n_elems;
     }
     // interface nodes: slots in ascending (set, patch) order, like iface_reduce_kernel

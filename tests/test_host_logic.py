@@ -125,3 +125,17 @@ def test_partitioned_matvec_equals_global(oracle, jf):
             yl = oracle.matfree(10, m.coords[p.local_nodes - 1], p.conn_local, ul).reshape(-1, 3)
             ref = y[p.local_nodes[:p.n_owned] - 1]
             assert np.abs(yl[:p.n_owned] - ref).max() < 1e-12 * np.abs(y).max()
+
+
+def test_partition_receive_lists_are_contiguous_ghost_order(jf):
+    """Precondition of the halo exchange fused into the patch kernel: concatenated over the neighbours in ascending rank
+    order, the receive lists are exactly the ghost nodes n_owned+1 .. n_local in order, so that ghost node g reads landing
+    slot g - n_owned (csrc/comm.cu: recv_contiguous)."""
+    import numpy as np
+    for m, world in ((jf.mesh.tet10_kuhn(4, 3, 9), 3), (jf.mesh.hex8_lattice(5, 4, 17, 0.1), 4), (jf.mesh.tet10_kuhn(6, 2, 2), 2)):
+        for rank in range(world):
+            p = jf.mesh.partition_mesh(m, world, rank)
+            got = np.concatenate([p.recv[s] for s in sorted(p.recv)]) if p.recv else np.zeros(0, dtype=np.int64)
+            assert np.array_equal(got, np.arange(p.n_owned + 1, p.local_nodes.size + 1))
+            for s, ids in p.send.items():
+                assert ids.min() >= 1 and ids.max() <= p.n_owned            # only owned nodes are sent

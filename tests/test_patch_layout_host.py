@@ -118,10 +118,17 @@ def test_lane_assignment_reduces_modelled_conflicts(hostcheck, jf):
     print(f"modelled 64-bit shared-memory wavefronts per patch and component: {before:.0f} -> {after:.0f} (ideal {ideal:.0f})")
 
 
-def test_ghost_aware_patch_order(hostcheck, oracle, jf):
-    """Partitioned mesh: patches that read ghost nodes (ids >= n_owned) are ordered last; results unchanged."""
-    m = jf.mesh.tet10_kuhn(10, 5, 5, 2.0, 1.0, 1.0)
+def test_ghost_aware_patch_order_and_landing_buffer(hostcheck, oracle, jf):
+    """Partitioned mesh (real partition of a 2-rank run, local numbering): patches that read ghost nodes (ids >= n_owned)
+    are ordered last and flagged; ghost values are taken from the landing buffer in ghost order (x's ghost entries are
+    poisoned in the replay); owned rows equal the global operator."""
+    m = jf.mesh.tet10_kuhn(6, 5, 12, 1.0, 1.0, 2.0)
     u = jf.mesh.test_vector(m.n_dofs)
-    n_owned = int(0.8 * m.n_nodes)
-    y, st = run(hostcheck, m, u, n_owned=n_owned)
-    assert relerr(y, oracle.matfree(10, m.coords, m.conn, u, par=(210e9, 0.3))) < 1e-12
+    yref = oracle.matfree(10, m.coords, m.conn, u, par=(210e9, 0.3)).reshape(-1, 3)
+    for rank in (0, 1):
+        p = jf.mesh.partition_mesh(m, 2, rank)
+        ml = jf.mesh.Mesh(10, m.coords[p.local_nodes - 1], p.conn_local)
+        ul = u.reshape(-1, 3)[p.local_nodes - 1].ravel()
+        y, _ = run(hostcheck, ml, ul, n_owned=p.n_owned)
+        own = y.reshape(-1, 3)[:p.n_owned]
+        assert relerr(own, yref[p.local_nodes[:p.n_owned] - 1]) < 1e-12
