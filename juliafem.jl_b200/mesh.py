@@ -1,4 +1,4 @@
-"""Deterministic synthetic meshes, a minimal Abaqus reader and the node-range partitioner.
+"""Deterministic synthetic meshes, minimal Abaqus / Gmsh readers and the node-range partitioner.
 
 Host-side helpers feeding the flat arrays the C ABI takes (include/jfem_b200.h).  All ids
 returned here are **1-based**, as at the reference's boundary (`Element.connectivity`,
@@ -179,6 +179,72 @@ def read_abaqus_inp(path: str, elem_type: int | None = None) -> Mesh:
     m = Mesh(elem_type, coords, conn)
     m.node_sets = {k: np.array(sorted(remap[n] for n in v if n in remap), dtype=np.int64) for k, v in nsets.items()}
     m.elem_sets = {k: np.array(sorted(eremap[e] for e in v if e in eremap), dtype=np.int64) for k, v in elsets.items()}
+    return m
+
+
+# Gmsh element type -> (nodes per element, kind); volume kinds are what the C ABI takes, surface kinds only feed node sets
+_GMSH_TYPES = {4: (4, "vol"), 5: (8, "vol"), 11: (10, "vol"), 2: (3, "surf"), 3: (4, "surf"), 9: (6, "surf"), 16: (8, "surf"), 10: (9, "surf")}
+_GMSH_TET10_TO_ABAQUS = [0, 1, 2, 3, 4, 5, 6, 7, 9, 8]   # Gmsh numbers edge (2-3) before (1-3); lagrange_generated.jl:261-262 the other way
+
+
+def read_gmsh_msh(path: str, elem_type: int | None = None) -> Mesh:
+    """Gmsh MSH 4.1 (ASCII) reader: $PhysicalNames, $Nodes, $Elements.
+
+    Same walk as the reference's reader (src/gmsh_reader.jl:28-155: entity blocks, node ids first then coordinates, the
+    entity tag of an element block names its group through $PhysicalNames), extended from Tet4 (type 4) to Hex8 (type 5)
+    and Tet10 (type 11, reordered to the reference's / Abaqus edge order).  Surface elements (triangles / quadrangles) are
+    not returned as elements; the nodes of every surface block go into ``node_sets`` under the block's physical name, which
+    is what Dirichlet / traction set-up needs.  Node ids are renumbered densely by sorted order (ext/JuliaFEMCUDAExt.jl:100-108)."""
+    names, nodes, vol, surf_nodes, groups = {}, {}, [], {}, {}
+    with open(path) as fh:
+        lines = iter(fh.read().splitlines())
+    for line in lines:
+        line = line.strip()
+        if line == "$MeshFormat":
+            ver = next(lines).split()
+            if not ver[0].startswith("4") or int(ver[1]) != 0:
+                raise ValueError(f"{path}: only ASCII MSH 4.x files are supported (found version {ver[0]}, file-type {ver[1]})")
+        elif line == "$PhysicalNames":
+            for _ in range(int(next(lines))):
+                dim, tag, name = next(lines).split(maxsplit=2)
+                names[(int(dim), int(tag))] = name.strip().strip('"')
+        elif line == "$Nodes":
+            nblocks = int(next(lines).split()[0])
+            for _ in range(nblocks):
+                nb = int(next(lines).split()[3])
+                ids = [int(next(lines)) for _ in range(nb)]
+                for nid in ids:
+                    nodes[nid] = [float(v) for v in next(lines).split()[:3]]
+        elif line == "$Elements":
+            nblocks = int(next(lines).split()[0])
+            for _ in range(nblocks):
+                dim, tag, gtype, nb = (int(v) for v in next(lines).split())
+                nn, kind = _GMSH_TYPES.get(gtype, (0, None))
+                name = names.get((dim, tag), f"Group_{tag}")
+                for _ in range(nb):
+                    parts = next(lines).split()
+                    if kind == "vol":
+                        c = [int(v) for v in parts[1:1 + nn]]
+                        if nn == 10:
+                            c = [c[k] for k in _GMSH_TET10_TO_ABAQUS]
+                        vol.append((nn, c))
+                        groups.setdefault(name, []).append(len(vol))
+                    elif kind == "surf":
+                        surf_nodes.setdefault(name, set()).update(int(v) for v in parts[1:1 + nn])
+    if not vol:
+        raise ValueError(f"{path}: no Tet4 / Hex8 / Tet10 elements found")
+    if elem_type is None:
+        elem_type = max(nn for nn, _ in vol)
+    keep = [i for i, (nn, _) in enumerate(vol) if nn == elem_type]
+    used = sorted({n for i in keep for n in vol[i][1]})
+    remap = {n: i + 1 for i, n in enumerate(used)}
+    coords = np.array([nodes[n] for n in used], dtype=np.float64)
+    conn = np.array([[remap[n] for n in vol[i][1]] for i in keep], dtype=np.int32)
+    eremap = {i + 1: k + 1 for k, i in enumerate(keep)}
+    m = Mesh(elem_type, coords, conn)
+    m.elem_sets = {k: np.array(sorted(eremap[e] for e in v if e in eremap), dtype=np.int64) for k, v in groups.items()}
+    m.elem_sets = {k: v for k, v in m.elem_sets.items() if v.size}
+    m.node_sets = {k: np.array(sorted(remap[n] for n in v if n in remap), dtype=np.int64) for k, v in surf_nodes.items()}
     return m
 
 

@@ -139,3 +139,72 @@ def test_partition_receive_lists_are_contiguous_ghost_order(jf):
             assert np.array_equal(got, np.arange(p.n_owned + 1, p.local_nodes.size + 1))
             for s, ids in p.send.items():
                 assert ids.min() >= 1 and ids.max() <= p.n_owned            # only owned nodes are sent
+
+
+GMSH_TET10 = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$PhysicalNames
+2
+2 7 "FixedEnd"
+3 1 "Body"
+$EndPhysicalNames
+$Entities
+0 0 1 1
+7 0 0 0 0 1 1 1 7 0
+1 0 0 0 1 1 1 1 1 0
+$EndEntities
+$Nodes
+2 11 1 40
+2 7 0 3
+1
+2
+3
+0 0 0
+1 0 0
+0 1 0
+3 1 0 8
+4
+10
+11
+12
+13
+14
+15
+40
+0 0 1
+0.5 0 0
+0.5 0.5 0
+0 0.5 0
+0 0 0.5
+0 0.5 0.5
+0.5 0 0.5
+9 9 9
+$EndNodes
+$Elements
+2 2 1 2
+2 7 2 1
+1 1 2 3
+3 1 11 1
+2 1 2 3 4 10 11 12 13 14 15
+$EndElements
+"""
+
+
+def test_gmsh_reader_tet10_order_sets_and_volume(tmp_path, oracle, jf):
+    """MSH 4.1: Tet10 edge order converted to the reference's (Gmsh lists edge 2-3 before 1-3), dense renumbering, physical
+    names -> element / node sets; the element's stiffness is symmetric with 6 rigid-body modes only if the order is right."""
+    import numpy as np
+    f = tmp_path / "one.msh"
+    f.write_text(GMSH_TET10)
+    m = jf.mesh.read_gmsh_msh(str(f))
+    assert m.elem_type == 10 and m.n_elems == 1 and m.n_nodes == 10          # node 40 is unused and dropped
+    X = m.coords[m.conn[0] - 1]
+    for k, (a, b) in enumerate([(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]):
+        assert np.allclose(X[4 + k], 0.5 * (X[a] + X[b]))                    # mid-edge nodes in the reference's order
+    assert list(m.elem_sets) == ["Body"] and list(m.elem_sets["Body"]) == [1]
+    assert list(m.node_sets["FixedEnd"]) == [1, 2, 3]
+    K = oracle.element(10, X)[0]
+    assert np.abs(K - K.T).max() < 1e-9 * np.abs(K).max()
+    rb = np.tile([1.0, 0.0, 0.0], 10)
+    assert np.abs(K @ rb).max() < 1e-9 * np.abs(K).max()
