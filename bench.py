@@ -48,6 +48,18 @@ def build_mesh(name, n_gpus=1):
     return mesh.hex8_lattice(nx, ny, (nz - 1) * n_gpus + 1, 1.0 / (nx - 1))
 
 
+def workload_label(name, n_gpus=1):
+    """'T1: Tet10 matrix-free K.u, <n> DOF, <m> elements' without building the mesh (same text as the GPU arm's config)."""
+    et, dims, _ = WORKLOADS[name]
+    if et == 10:
+        cx, cy, cz = dims[0], dims[1], dims[2] * n_gpus
+        nd, ne = 3 * (2 * cx + 1) * (2 * cy + 1) * (2 * cz + 1), 6 * cx * cy * cz
+    else:
+        nx, ny, nz = dims[0], dims[1], (dims[2] - 1) * n_gpus + 1
+        nd, ne = 3 * nx * ny * nz, (nx - 1) * (ny - 1) * (nz - 1)
+    return f"{name}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {nd} DOF, {ne} elements"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -132,7 +144,9 @@ def run_reference(args, rank):
     cb = cpu_baseline(args.workload, seconds=10.0)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload + " (bounded sample, see cpu_baseline.sample)"},
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_label(args.workload) + " -- CPU arm: assembled CSR K.v of the reference on a bounded sample of this mesh "
+                                  "(see cpu_baseline.sample)"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
