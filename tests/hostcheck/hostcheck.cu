@@ -141,3 +141,20 @@ extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, 
     stats[6] = (double)hif.n_partials; stats[7] = (double)sets[CLASS_AFFINE].n_elems;
     return 0;
 }
+
+// wall time of the patch construction alone (setup cost study; not used by the tests)
+#include <chrono>
+extern "C" double hostcheck_build_seconds(int nnpe, long long n_nodes, long long n_elems, const double *coords, const int32_t *conn, int EP,
+                                          int lane_window, long long n_owned) {
+    MeshHost m;
+    m.nnpe = nnpe; m.n_nodes = n_nodes; m.n_elems = n_elems;
+    m.coords.assign(coords, coords + 3 * n_nodes);
+    m.conn.assign(conn, conn + (size_t)nnpe * n_elems);
+    m.fixed.assign(3 * n_nodes, 0);
+    auto t0 = std::chrono::steady_clock::now();
+    classify_elements(m, true);
+    PatchSetHost sets[N_CLASSES];
+    InterfaceHost hif;
+    if (build_patch_sets(m, EP, true, lane_window, n_owned, sets, hif) != JFEM_OK) return -1.0;
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
