@@ -5,6 +5,10 @@ A "step" is ONE matrix-free K.u over the whole mesh (BASELINE.json configs[1]: T
 1 075 275 DOF; for N GPUs the box grows to 88x22x(22N) cells and is slab-partitioned by contiguous node ranges, i.e.
 weak scaling).  Timed with CUDA events on the stream the kernels are launched on; L2 is flushed between timed steps
 (a 512 MiB buffer is overwritten), because the T1 working set (~40 MB) would otherwise sit in the 126 MB L2.
+After an untimed clock spin-up (--spinup seconds of the same step, same count on every rank) and W warm-up steps, the K
+timed steps (flush, event, K.u, event) are captured once and replayed as ONE CUDA graph, bracketed by barrier +
+synchronize, so that no host launch sits between the steps (--graph 0: per-step host launches; automatic fallback if the
+capture fails).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload T1|T10|H100|...]
 
