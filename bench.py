@@ -261,9 +261,9 @@ def main():
         # The K timed steps (L2 flush, event, K.u, event) are captured once and replayed as ONE graph launch: every rank's
         # GPU then runs its K steps back to back with no host in the loop, so a late host launch on one rank cannot stall
         # its neighbours at the halo gate.  Same kernels, same events, same barrier + synchronize bracket.
-        ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(args.steps)]
         ok = 1.0
         try:
+            ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(args.steps)]
             g = torch.cuda.CUDAGraph()
             cap = torch.cuda.Stream()
             torch.cuda.synchronize()
