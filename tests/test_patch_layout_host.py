@@ -132,3 +132,18 @@ def test_ghost_aware_patch_order_and_landing_buffer(hostcheck, oracle, jf):
         y, _ = run(hostcheck, ml, ul, n_owned=p.n_owned)
         own = y.reshape(-1, 3)[:p.n_owned]
         assert relerr(own, yref[p.local_nodes[:p.n_owned] - 1]) < 1e-12
+
+
+def test_tiny_and_empty_meshes(hostcheck, oracle, jf):
+    """Edge cases: one element (a single, partial patch), two elements sharing a face, and a mesh without elements
+    (every node is an orphan: y = 0)."""
+    for et, m in ((10, jf.mesh.tet10_kuhn(1, 1, 1)), (8, jf.mesh.hex8_lattice(2, 2, 2, 0.5)), (4, jf.mesh.tet4_kuhn(1, 1, 1))):
+        for ne in (1, min(2, m.n_elems)):
+            sub = jf.mesh.Mesh(et, m.coords, m.conn[:ne])
+            u = jf.mesh.test_vector(sub.n_dofs)
+            y, st = run(hostcheck, sub, u, EP=128)
+            assert st[3] == 1                                     # one patch
+            assert relerr(y, oracle.matfree(et, sub.coords, sub.conn, u, par=(210e9, 0.3))) < 1e-12
+    empty = jf.mesh.Mesh(10, jf.mesh.tet10_kuhn(1, 1, 1).coords, np.zeros((0, 10), dtype=np.int32))
+    y, st = run(hostcheck, empty, np.ones(empty.n_dofs))
+    assert st[3] == 0 and np.all(y == 0.0)
