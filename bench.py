@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (jfem_set_option), repeatable")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--spinup", type=float, default=0.4, help="seconds of untimed load before the warm-up steps (clock ramp)")
+    ap.add_argument("--spinup", type=float, default=0.8, help="seconds of untimed load before the warm-up steps (clock ramp)")
     ap.add_argument("--graph", type=int, default=-1, help="1: replay the timed loop as one CUDA graph (no host launch jitter between "
                     "ranks); 0: launch every step from the host; default: 1")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
