@@ -145,7 +145,7 @@ extern "C" int hostcheck_matvec(int nnpe, long long n_nodes, long long n_elems, 
 // wall time of the patch construction alone (setup cost study; not used by the tests)
 #include <chrono>
 extern "C" double hostcheck_build_seconds(int nnpe, long long n_nodes, long long n_elems, const double *coords, const int32_t *conn, int EP,
-                                          int lane_window, long long n_owned) {
+                                          int lane_window, long long n_owned, double *quality) {
     MeshHost m;
     m.nnpe = nnpe; m.n_nodes = n_nodes; m.n_elems = n_elems;
     m.coords.assign(coords, coords + 3 * n_nodes);
@@ -156,5 +156,10 @@ extern "C" double hostcheck_build_seconds(int nnpe, long long n_nodes, long long
     PatchSetHost sets[N_CLASSES];
     InterfaceHost hif;
     if (build_patch_sets(m, EP, true, lane_window, n_owned, sets, hif) != JFEM_OK) return -1.0;
+    if (quality) {   // patches, nodes per patch (mean, max), interface nodes, partial slots, max coordinate nodes, blob stride
+        const PatchSetHost &S = sets[CLASS_AFFINE].n_elems ? sets[CLASS_AFFINE] : sets[CLASS_GENERAL];
+        quality[0] = S.n_patches; quality[1] = S.n_patches ? (double)S.pnode_ptr[S.n_patches] / S.n_patches : 0; quality[2] = S.max_nodes;
+        quality[3] = (double)hif.inodes.size(); quality[4] = (double)hif.n_partials; quality[5] = S.max_nx; quality[6] = S.L.stride;
+    }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
