@@ -146,6 +146,7 @@ class ElasticitySolution:     # src/backend/abstract.jl:138-145
     residual: float
     solve_time: float
     history: list
+    converged: bool = True
 
 
 class Physics:
@@ -311,11 +312,19 @@ def solve_backend_(data: ElasticityDataGPU, physics: Physics = None, tol=1e-6, m
         u0 = data.prescribed.copy()
         u, nit, cgit, res, hist = h.newton_krylov(data.f_ext, u0, newton_tol=newton_tol, max_newton=max_newton,
                                                   max_cg_per_newton=max_cg_per_newton, forcing_power=forcing_power, forcing_max=forcing_max)
+        data.converged = bool(res < newton_tol)
+        if not data.converged:      # the reference prints "Newton did not converge" and returns (ext:850-853)
+            import warnings
+            warnings.warn(f"Newton-Krylov did not converge in {nit} iterations: ||R|| = {res:.3e} >= {newton_tol:.3e}")
         return u, nit, cgit, res, hist
     b = data.f_ext
     if np.any(data.prescribed):
         b = b - h.matvec(data.prescribed)          # lifting: f_I - K_IB u_B   (src/solvers.jl:205-210)
     x, it, res = h.cg(b, tol=tol, relative=False, max_iter=max_iter)
+    data.converged = bool(res < tol)
+    if not data.converged:          # ext:630 "CG did not converge"
+        import warnings
+        warnings.warn(f"CG did not converge in {it} iterations: sqrt(r.r) = {res:.3e} >= {tol:.3e}")
     u = x + data.prescribed
     rn = float(np.sqrt(np.sum(np.delete(b, data.fixed_dofs - 1) ** 2))) if data.fixed_dofs.size else float(np.linalg.norm(b))
     return u, 1, it, res, [(it, rn, min(forcing_max, rn ** forcing_power) if rn > 0 else 0.0)]
@@ -332,7 +341,7 @@ def solve_(physics: Physics, backend=None, time=0.0, tol=1e-6, max_iter=1000, ne
                                                  max_newton=max_newton, max_cg_per_newton=max_cg_per_newton)
     finally:
         data.close()
-    return ElasticitySolution(u, nit, cgit, res, _time.perf_counter() - t0, hist)
+    return ElasticitySolution(u, nit, cgit, res, _time.perf_counter() - t0, hist, getattr(data, "converged", True))
 
 
 # ------------------------------------------------------------------------------------------------ seam 2
@@ -358,6 +367,7 @@ class Assembly:               # src/assembly/problems.jl:14-40 (fields used on t
         self.K = None
         self.f = None
         self.u = None
+        self.la = None
 
 
 class Problem:
@@ -454,22 +464,57 @@ def assemble_(problem: Problem, time=0.0, u=None, symmetrise=False, device=0):
     return problem
 
 
+class ConvergenceError(RuntimeError):
+    """Nonlinear iteration did not converge (the reference throws from the Nonlinear solver, src/solvers.jl:617-619)."""
+
+
 class Analysis:
-    """Analysis(Linear, model, fixed)  (src/analysis.jl:7-13)"""
+    """Analysis(Linear, model, fixed)  (src/analysis.jl:7-13).  After run_: u, reactions, converged, residual,
+    iterations (Newton), cg_iterations; analysis("displacement", time) returns {node id: vector} like the reference's
+    field access (examples/linear_static.jl:131)."""
 
     def __init__(self, kind, *problems, name="analysis"):
         self.properties = kind() if isinstance(kind, type) else kind
         self.problems = list(problems)
         self.name = name
         self.u = None
+        self.reactions = None
         self.iterations = 0
         self.cg_iterations = 0
+        self.converged = False
+        self.residual = float("nan")
+        self.history = []
+
+    def __call__(self, field_name, time=0.0):
+        model = next(p for p in self.problems if isinstance(p.properties, Elasticity))
+        if self.u is None:
+            raise KeyError(f"{field_name}: analysis has not been run")
+        if field_name == "displacement":
+            return nodal_displacements(model, self.u)
+        if field_name == "reaction force":
+            return nodal_displacements(model, self.reactions)
+        if field_name in ("stress", "strain"):
+            return model.postprocess(field_name)
+        raise KeyError(field_name)
 
 
-def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0):
+def _free_norm(b, fixed_dofs):
+    if len(fixed_dofs):
+        b = b.copy()
+        b[np.asarray(fixed_dofs) - 1] = 0.0
+    return float(np.linalg.norm(b))
+
+
+def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0, newton_tol=None, strict=True):
     """run!(analysis)  (src/solvers.jl:641 Linear, :575 Nonlinear).  The direct LDLt of solve!(...,Val{1})
     (src/solvers.jl:192-216) is replaced by projected CG on the device with the same elimination semantics:
-    u_B = g, K_II u_I = f_I - K_IB u_B.  Default stop: ||r|| <= 1e-8 ||b|| (north_star)."""
+    u_B = g, K_II u_I = f_I - K_IB u_B, and the reaction forces la = K u - f on the constrained dofs (:211-216 returns
+    them as the Lagrange multipliers).  Default stop: ||r|| <= 1e-8 ||b|| (north_star).
+    Convergence is checked: a CG solve that stops at max_iter warns (as ext/JuliaFEMCUDAExt.jl:630 does), a Newton
+    iteration that does not reach its tolerance raises ConvergenceError like src/solvers.jl:617-619 (strict=False
+    downgrades that to a warning).  The Newton tolerance is relative to ||f_ext|| of the free dofs (an absolute residual
+    is meaningless across unit systems): newton_tol defaults to max(tol, 1e-10)."""
+    import warnings
     field_problems = [p for p in analysis.problems if isinstance(p.properties, Elasticity)]
     boundary = [p for p in analysis.problems if isinstance(p.properties, Dirichlet)]
     if len(field_problems) != 1:
@@ -479,17 +524,39 @@ def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0)
     d = _ensure_data(model, boundary, device=device)
     h = d.handle
     if isinstance(analysis.properties, Nonlinear) or model.properties.finite_strain or isinstance(model.material, (NeoHookean, PerfectPlasticity)):
-        u, nit, cgit, res, hist = h.newton_krylov(d.f_ext, d.prescribed.copy(), newton_tol=max(tol, 1e-12) if not relative else 1e-6,
-                                                  max_newton=max(20, getattr(analysis.properties, "max_iterations", 10)),
+        scale = _free_norm(d.f_ext - (h.matvec(d.prescribed) if np.any(d.prescribed) else 0.0), d.fixed_dofs)
+        rel = max(tol, 1e-10) if newton_tol is None else newton_tol
+        ntol = rel * (scale if scale > 0 else 1.0)
+        max_newton = max(20, getattr(analysis.properties, "max_iterations", 10))
+        u, nit, cgit, res, hist = h.newton_krylov(d.f_ext, d.prescribed.copy(), newton_tol=ntol, max_newton=max_newton,
                                                   max_cg_per_newton=max_iter, forcing_max=1e-3)
-        analysis.iterations, analysis.cg_iterations = nit, cgit
+        analysis.iterations, analysis.cg_iterations, analysis.history = nit, cgit, hist
+        analysis.converged = bool(res < ntol)
+        if not analysis.converged:
+            msg = f"nonlinear iteration did not converge in {nit} iterations: ||R|| = {res:.3e} > {ntol:.3e}"
+            if strict:
+                analysis.u, analysis.residual = u, res
+                raise ConvergenceError(msg)
+            warnings.warn(msg)
+        fint = h.internal_force(u)
     else:
         b = d.f_ext - (h.matvec(d.prescribed) if np.any(d.prescribed) else 0.0)
         x, it, res = h.cg(b, tol=tol, relative=relative, max_iter=max_iter)
         u = x + d.prescribed
+        thr = tol * _free_norm(b, d.fixed_dofs) if relative else tol
         analysis.iterations, analysis.cg_iterations = 1, it
+        analysis.converged = bool(res <= thr if relative else res < thr)
+        if not analysis.converged:
+            warnings.warn(f"CG did not converge in {it} iterations: ||r|| = {res:.3e} > {thr:.3e}")
+        fint = h.matvec(u)
+    analysis.residual = res
     analysis.u = u
+    # reaction forces on the constrained dofs: la = K u - f (src/solvers.jl:211-216), zero elsewhere
+    analysis.reactions = np.zeros(d.n_dofs)
+    if d.fixed_dofs.size:
+        analysis.reactions[d.fixed_dofs - 1] = (fint - d.f_ext)[d.fixed_dofs - 1]
     model.assembly.u = u
+    model.assembly.la = analysis.reactions
     return analysis
 
 

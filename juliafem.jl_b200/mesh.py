@@ -248,6 +248,103 @@ def read_gmsh_msh(path: str, elem_type: int | None = None) -> Mesh:
     return m
 
 
+# Code Aster (.med) element names and node orders -> the reference's (Abaqus) conventions.
+# Names: src/io/aster_reader.jl:27-47 (`med_element_names`); permutations: :16-23 (`med_connectivity`), applied as
+# new = old[perm] (src/preprocess.jl:301-309).
+_MED_TYPES = {"TE4": (TET4, [4, 3, 1, 2]), "T10": (TET10, [4, 3, 1, 2, 10, 7, 8, 9, 6, 5]), "HE8": (HEX8, [4, 8, 7, 3, 1, 5, 6, 2])}
+
+
+def read_med(path: str, mesh_name: str | None = None, elem_type: int | None = None, reorder_element_connectivity: bool = True) -> Mesh:
+    """`aster_read_mesh(filename, mesh_name)` for volume meshes (src/io/aster_reader.jl:56-82 over
+    src/readers/read_aster_mesh.jl:118-222): nodes from ENS_MAA/<mesh>/<increment>/NOE/{COO,NUM,FAM} (coordinates are
+    stored non-interlaced: all x, then all y, then all z, :127-128), elements from .../MAI/<TE4|T10|HE8>/{NOD,NUM,FAM}
+    (connectivity non-interlaced as well, :149-150), node / element sets from the family groups FAS/<mesh>/{NOEUD,ELEME}
+    (family 0 = "OTHER", :69, :131-133).  Lower-dimensional cells (SE3, TR6, ...: the edge and surface meshes FreeCAD
+    exports, which examples/linear_static.jl:35-39 filters out) are not returned.  The HDF5 container is parsed by
+    h5lite (no h5py in this image).  Node ids are renumbered densely in ascending order of the file's ids."""
+    from . import h5lite
+    tree = h5lite.read(path)
+    names = sorted(tree["FAS"].keys()) if "FAS" in tree else sorted(tree["ENS_MAA"].keys())
+    if mesh_name is None:
+        if len(names) != 1:
+            raise ValueError("several meshes found from med, pick one: " + ", ".join(names))
+        mesh_name = names[0]
+    elif mesh_name not in names:
+        raise ValueError(f"Mesh {mesh_name} not found. Available meshes: " + ", ".join(names))
+    incs = tree["ENS_MAA"][mesh_name]
+    incs = {k: v for k, v in incs.items() if isinstance(v, dict)}
+    if len(incs) != 1:
+        raise ValueError("exactly one mesh increment expected")
+    inc = next(iter(incs.values()))
+
+    def family_names(kind):
+        out = {0: ["OTHER"]}
+        fas = tree.get("FAS", {}).get(mesh_name, {}).get(kind) or {}
+        for i, k in enumerate(sorted(fas.keys())):
+            fid = int(k.split("_")[1]) if k.startswith("FAM") else -(i + 1)
+            gro = (fas[k] or {}).get("GRO") if isinstance(fas[k], dict) else None
+            nom = gro.get("NOM") if gro else None
+            if nom is None:
+                out[fid] = [""]
+            else:
+                out[fid] = [bytes(np.asarray(r, dtype=np.int8).astype(np.uint8)).split(b"\0")[0].decode("ascii").strip() for r in np.atleast_2d(nom)]
+        return out
+
+    noe = inc["NOE"]
+    nn = int(noe["FAM"].size)
+    dim = noe["COO"].size // nn
+    coords = np.zeros((nn, 3))
+    coords[:, :dim] = noe["COO"].reshape(dim, nn).T
+    node_ids = np.asarray(noe["NUM"], dtype=np.int64) if noe.get("NUM") is not None else np.arange(1, nn + 1, dtype=np.int64)
+    order = np.argsort(node_ids, kind="stable")
+    remap = {int(n): i + 1 for i, n in enumerate(node_ids[order])}
+    coords = coords[order]
+    nsets: dict = {}
+    nfam = family_names("NOEUD")
+    for fam, nid in zip(np.asarray(noe["FAM"])[order], range(1, nn + 1)):
+        for name in nfam.get(int(fam), ["OTHER"]):
+            nsets.setdefault(name, []).append(nid)
+    mai = inc.get("MAI", {})
+    vol = [k for k in mai if k in _MED_TYPES and (elem_type is None or _MED_TYPES[k][0] == elem_type)]
+    if not vol:
+        raise ValueError("no TE4 / T10 / HE8 cells in " + path)
+    key = max(vol, key=lambda k: mai[k]["FAM"].size)
+    et, perm = _MED_TYPES[key]
+    ne = int(mai[key]["FAM"].size)
+    conn = np.asarray(mai[key]["NOD"], dtype=np.int64).reshape(et, ne).T
+    if reorder_element_connectivity:
+        conn = conn[:, np.array(perm) - 1]
+    lut = np.zeros(int(node_ids.max()) + 1, dtype=np.int64)
+    lut[node_ids[order]] = np.arange(1, nn + 1)
+    conn = lut[conn].astype(np.int32)
+    elem_ids = np.asarray(mai[key]["NUM"], dtype=np.int64) if mai[key].get("NUM") is not None else np.arange(1, ne + 1)
+    eorder = np.argsort(elem_ids, kind="stable")
+    conn = np.ascontiguousarray(conn[eorder])
+    esets: dict = {}
+    efam = family_names("ELEME")
+    for i, fam in enumerate(np.asarray(mai[key]["FAM"])[eorder]):
+        for name in efam.get(int(fam), ["OTHER"]):
+            esets.setdefault(name, []).append(i + 1)
+    m = Mesh(et, coords, conn)
+    m.node_sets = {k: np.array(v, dtype=np.int64) for k, v in nsets.items()}
+    m.elem_sets = {k: np.array(v, dtype=np.int64) for k, v in esets.items()}
+    return m
+
+
+def find_nearest_nodes(mesh: Mesh, point, npts: int = 1, node_set=None) -> np.ndarray:
+    """`find_nearest_nodes(mesh, coords, npts; node_set)` (src/preprocess.jl:270-282): 1-based ids of the npts nodes
+    closest to `point`, nearest first."""
+    ids = np.arange(1, mesh.n_nodes + 1) if node_set is None else np.asarray(mesh.node_sets[node_set], dtype=np.int64)
+    d = np.linalg.norm(mesh.coords[ids - 1] - np.asarray(point, dtype=np.float64)[None, :], axis=1)
+    return ids[np.argsort(d, kind="stable")[:npts]]
+
+
+def nodes_at_plane(mesh: Mesh, axis: int, distance: float, radius: float = 6.0) -> np.ndarray:
+    """1-based ids of the nodes with |x_axis - distance| <= radius: the helper examples/linear_static.jl:46-54 defines
+    (`isapprox(coords[vector_id], distance, atol=radius)`); axis is 0-based here."""
+    return np.nonzero(np.abs(mesh.coords[:, axis] - distance) <= radius)[0].astype(np.int64) + 1
+
+
 def clamp_dofs(mesh: Mesh, axis: int = 0, value: float = 0.0, tol: float = 1e-12) -> np.ndarray:
     """1-based dof ids of all three components of nodes on the plane x_axis == value
     (demos/cantilever_physics_gpu.jl:88-93 clamps x = 0)."""

@@ -594,3 +594,31 @@ int orc_colouring(int et, int64_t n_nodes, int64_t n_elems, const int32_t *conn,
     free(ptr); free(fill); free(n2e);
     return ncol;
 }
+
+/* ------------------------------------------------------------------ external loads (f_ext) */
+
+/* Consistent body load, src/problems_elasticity.jl:412-426: per Gauss point f_ext[3k+i] += w N_k b_i with
+ * w = ip.weight * detJ ("displacement load" vector or "displacement load i" components).
+ * NOTE on :418-425: as shipped, the per-component branch ASSIGNS (`f_ext[j] = b * f_buffer_dim[i]`, inner `i`
+ * shadowing the component index), which would keep only the last Gauss point and always write component 1.
+ * The reference's own end-to-end answer (examples/linear_static.jl:133, max|u| = 2.4052929896922337) is reproduced
+ * to 6e-12 by the ACCUMULATING form below and not by the literal one (0.61 instead of 2.41), so the accumulating
+ * form -- what the vector branch :412-416 does -- is the specification.  b: per-element 3 values (n_elems x 3). */
+void orc_body_load(int et, int64_t n_nodes, int64_t n_elems, const double *X, const int32_t *conn, const double *b, double *f) {
+    int nn = et;
+    double w[ORC_MAXGP], xi[ORC_MAXGP * 3];
+    int ng = orc_quadrature(et, w, xi);
+    memset(f, 0, sizeof(double) * 3 * n_nodes);
+    for (int64_t e = 0; e < n_elems; e++) {
+        double Xe[ORC_MAXN * 3];
+        for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) Xe[k * 3 + c] = X[(int64_t)conn[e * nn + k] * 3 + c];
+        for (int g = 0; g < ng; g++) {
+            double N[ORC_MAXN], dN[ORC_MAXN * 3], J[9] = {0};
+            orc_shape_N(et, xi + 3 * g, N);
+            orc_shape_dN(et, xi + 3 * g, dN);
+            for (int i = 0; i < nn; i++) for (int a = 0; a < 3; a++) for (int c = 0; c < 3; c++) J[a * 3 + c] += dN[i * 3 + a] * Xe[i * 3 + c];
+            double wd = w[g] * det3(J);
+            for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) f[(int64_t)conn[e * nn + k] * 3 + c] += wd * N[k] * b[e * 3 + c];
+        }
+    }
+}

@@ -66,6 +66,7 @@ def lib():
         L.orc_cg_csr.restype = C.c_int
         L.orc_colouring.argtypes = [C.c_int, C.c_int64, C.c_int64, _ip, _ip]
         L.orc_colouring.restype = C.c_int
+        L.orc_body_load.argtypes = [C.c_int, C.c_int64, C.c_int64, _dp, _ip, _dp, _dp]
     return _lib
 
 
@@ -224,3 +225,13 @@ def colouring(et, n_nodes, conn):
     col = np.zeros(c0.shape[0], dtype=np.int32)
     n = lib().orc_colouring(et, n_nodes, c0.shape[0], c0, col)
     return col, n
+
+
+def body_load(et, coords, conn, b):
+    """Consistent body load f_ext (src/problems_elasticity.jl:412-426); b = 3 values or (n_elems, 3)."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    c0 = _conn0(conn)
+    bb = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64), (c0.shape[0], 3)))
+    f = np.zeros(3 * coords.shape[0])
+    lib().orc_body_load(et, coords.shape[0], c0.shape[0], coords, c0, bb, f)
+    return f

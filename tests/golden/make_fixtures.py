@@ -5,6 +5,11 @@
 * tet10_fixture.npz -- the unstructured Tet10 mesh of the reference's own test fixture
   test/test_problems_contact_3d/tet10.inp (607 nodes, 269 C3D10), parsed with juliafem.jl_b200.mesh.read_abaqus_inp
   and stored as flat arrays (coords, 1-based conn, element sets) so that GPU-box tests need no /root/reference.
+* linear_static_smp18.npz -- the mesh of the reference's end-to-end example examples/linear_static.jl
+  (examples/linear_static/JuliaFEMSMP18.med: 14 078 nodes, 6 131 Tet10 after the edge/surface cells are dropped), read with
+  juliafem.jl_b200.mesh.read_med (pure-Python HDF5 subset, h5lite.py) exactly as aster_read_mesh does, incl. the
+  Code Aster -> Abaqus node reordering.  The expected answer of that example (max |u| = 2.4052929896922337,
+  examples/linear_static.jl:133) is in pins.json.
 * pins.json -- the known-answer values that survive in the reference's docs/comments; each
   entry cites its source.  They are literals, not computed from our code.
 """
@@ -25,7 +30,15 @@ def main():
     assert m.elem_type == 10 and m.n_nodes == 607 and m.n_elems == 269, (m.n_nodes, m.n_elems)
     np.savez_compressed(os.path.join(HERE, "tet10_fixture.npz"), coords=m.coords, conn=m.conn,
                         **{"elset_" + k: v for k, v in m.elem_sets.items()})
+    ms = mesh.read_med(os.path.join(REF, "examples/linear_static/JuliaFEMSMP18.med"))
+    assert ms.elem_type == 10 and ms.n_nodes == 14078 and ms.n_elems == 6131, (ms.n_nodes, ms.n_elems)
+    np.savez_compressed(os.path.join(HERE, "linear_static_smp18.npz"), coords=ms.coords, conn=ms.conn)
     pins = {
+        "linear_static": {"source": "examples/linear_static.jl:23-100,133 on examples/linear_static/JuliaFEMSMP18.med",
+                          "E": 208.0e3, "nu": 0.30, "displacement_load_1": 1.0,
+                          "fixed": "all three components of the nodes with |y - 50| <= 6 and of the 3 nodes nearest to (165, 88, 10)",
+                          "max_u_norm": 2.4052929896922337, "isapprox_rtol": 1.4901161193847656e-08,
+                          "n_nodes": 14078, "n_tet10": 6131},
         "le_uniaxial": {"source": "docs/book/linear_elastic_implementation.md:187-200", "E": 200e9, "nu": 0.3,
                         "eps": [1e-3, 0, 0, 0, 0, 0], "sigma11_MPa": 269.2307692, "sigma22_MPa": 115.3846154},
         "le_pure_shear": {"source": "docs/book/linear_elastic_implementation.md:205-214", "E": 200e9, "nu": 0.3,

@@ -113,3 +113,41 @@ def test_unsupported_element_refused_like_reference(jf):
     p.elements.append(el)
     with pytest.raises(ValueError):
         A.assemble_(p, 0.0)
+
+
+def test_linear_static_example_end_to_end(oracle, jf):
+    """X1 = BASELINE.json configs[0]: examples/linear_static.jl through the reference-facing interface on the GPU.
+    Mesh = the committed copy of JuliaFEMSMP18.med (tests/golden/make_fixtures.py); expected max |u| =
+    2.4052929896922337 (examples/linear_static.jl:133; the reference tests it with isapprox, rtol 1.5e-8)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from juliafem.jl_b200 import api as A
+    from test_oracle_pins import _linear_static_case
+    m, fixed_dofs, pin = _linear_static_case()
+    els = [A.Element(A.Tet10, c, fields={"geometry": m.coords[c - 1].T}) for c in m.conn]
+    model = A.Problem(A.Elasticity, "OTHER", 3)
+    A.update_(els, "youngs modulus", 208.0e3)                  # examples/linear_static.jl:28-30
+    A.update_(els, "poissons ratio", 0.30)
+    A.update_(els, "density", 7.80e-9)
+    A.add_elements_(model, els)
+    A.update_(els, "displacement load 1", 1.0)                 # :85
+    nodes = np.union1d(jf.mesh.nodes_at_plane(m, 1, 50.0), jf.mesh.find_nearest_nodes(m, [165.0, 88.0, 10], 3))   # :46-72
+    fixed = A.Problem(A.Dirichlet, "fixed", 3, "displacement")
+    fel = [A.Element(A.Poi1, [int(n)]) for n in nodes]
+    for c in (1, 2, 3):
+        A.update_(fel, f"displacement {c}", 0.0)
+    A.add_elements_(fixed, fel)
+    analysis = A.Analysis(A.Linear, model, fixed)
+    A.run_(analysis, tol=1e-12, relative=True, max_iter=200000)
+    assert analysis.converged and analysis.residual <= 1e-12 * np.linalg.norm(model._data.f_ext[np.setdiff1d(np.arange(m.n_dofs), fixed_dofs - 1)]) * 1.01
+    u = analysis("displacement", 0.0)                          # :131: Dict node id -> displacement vector
+    umax = max(np.linalg.norm(v) for v in u.values())
+    assert abs(umax / pin["max_u_norm"] - 1.0) < 1e-8, umax
+    # and the whole field against the oracle's eliminated direct solve
+    rp, ci, vals, _ = oracle.assemble_csr(10, m.coords, m.conn, par=(pin["E"], pin["nu"]), symmetrise=True)
+    K = sp.csr_matrix((vals, ci, rp))
+    f = oracle.body_load(10, m.coords, m.conn, (1.0, 0.0, 0.0))
+    free = np.setdiff1d(np.arange(m.n_dofs), fixed_dofs - 1)
+    uref = np.zeros(m.n_dofs)
+    uref[free] = spla.splu(K[free][:, free].tocsc()).solve(f[free])
+    assert relerr(analysis.u, uref) < 1e-8

@@ -241,3 +241,62 @@ def test_colouring_is_valid(oracle, jf):
     for c in range(n):
         nodes = m.conn[col == c].ravel()
         assert nodes.size == np.unique(nodes).size
+
+
+def _linear_static_case():
+    """Mesh, fixed dofs (1-based) and pin of examples/linear_static.jl:23-100,133 (fixture: tests/golden/make_fixtures.py)."""
+    from juliafem.jl_b200 import mesh
+    z = np.load(os.path.join(HERE, "golden", "linear_static_smp18.npz"))
+    m = mesh.Mesh(10, z["coords"], z["conn"])
+    nodes = np.union1d(mesh.nodes_at_plane(m, 1, 50.0, 6.0), mesh.find_nearest_nodes(m, [165.0, 88.0, 10.0], 3))
+    fixed = np.sort((3 * (nodes[:, None] - 1) + np.arange(1, 4)[None, :]).ravel())
+    return m, fixed, PINS["linear_static"]
+
+
+def test_linear_static_end_to_end_pin(oracle):
+    """The one reference-held number for the whole assemble -> eliminate -> solve path: the oracle's K (Tet10 GLTET4,
+    3(n-1)+c numbering, (K+K')/2), consistent body load and the elimination of src/solvers.jl:205-210 with a direct
+    solve reproduce examples/linear_static.jl:133 far inside the reference's own isapprox tolerance."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m, fixed, pin = _linear_static_case()
+    assert (m.n_nodes, m.n_elems) == (pin["n_nodes"], pin["n_tet10"]) and fixed.size == 3 * 1939
+    rp, ci, vals, _ = oracle.assemble_csr(10, m.coords, m.conn, par=(pin["E"], pin["nu"]), symmetrise=True)
+    K = sp.csr_matrix((vals, ci, rp))
+    f = oracle.body_load(10, m.coords, m.conn, (pin["displacement_load_1"], 0.0, 0.0))
+    free = np.setdiff1d(np.arange(m.n_dofs), fixed - 1)
+    u = np.zeros(m.n_dofs)
+    u[free] = spla.splu(K[free][:, free].tocsc()).solve(f[free])
+    umax = np.linalg.norm(u.reshape(-1, 3), axis=1).max()
+    assert abs(umax / pin["max_u_norm"] - 1.0) < 1e-9, umax
+    # the literal (assigning) form of src/problems_elasticity.jl:418-425 does NOT give the reference's answer
+    w, xi = oracle.quadrature(10)
+    X = m.coords[m.conn - 1]
+    J = np.einsum("ia,eib->eab", oracle.shape_dN(10, xi[-1]), X)
+    flit = np.zeros(m.n_dofs)
+    np.add.at(flit, 3 * (m.conn - 1), (w[-1] * np.linalg.det(J))[:, None] * oracle.shape_N(10, xi[-1])[None, :])
+    ul = np.zeros(m.n_dofs)
+    ul[free] = spla.splu(K[free][:, free].tocsc()).solve(flit[free])
+    assert abs(np.linalg.norm(ul.reshape(-1, 3), axis=1).max() / pin["max_u_norm"] - 1.0) > 0.5
+
+
+def test_body_load_total_and_python_mirror(oracle):
+    from juliafem.jl_b200 import mesh
+    m = mesh.tet10_kuhn(3, 2, 2, 3.0, 1.0, 2.0)
+    f = oracle.body_load(10, m.coords, m.conn, (1.0, -2.0, 0.5))
+    assert np.allclose(f.reshape(-1, 3).sum(0), np.array([1.0, -2.0, 0.5]) * 6.0, rtol=1e-13)
+    h = mesh.hex8_lattice(4, 3, 3, 0.5)
+    f = oracle.body_load(8, h.coords, h.conn, (0.0, 0.0, 9.81))
+    assert abs(f[2::3].sum() - 9.81 * 1.5 * 1.0 * 1.0) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/examples/linear_static/JuliaFEMSMP18.med"), reason="reference tree not present")
+def test_med_reader_matches_committed_fixture():
+    """h5lite + mesh.read_med on the reference's .med file == the committed npz (so the fixture is what the file holds)."""
+    from juliafem.jl_b200 import mesh
+    m = mesh.read_med("/root/reference/examples/linear_static/JuliaFEMSMP18.med")
+    z = np.load(os.path.join(HERE, "golden", "linear_static_smp18.npz"))
+    assert np.array_equal(m.coords, z["coords"]) and np.array_equal(m.conn, z["conn"])
+    assert set(m.elem_sets) == {"OTHER"} and m.elem_sets["OTHER"].size == m.n_elems
+    with pytest.raises(ValueError):
+        mesh.read_med("/root/reference/examples/linear_static/JuliaFEMSMP18.med", mesh_name="nope")
