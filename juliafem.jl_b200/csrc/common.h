@@ -67,12 +67,20 @@ struct DevBuf {
 };
 
 // Per-patch metadata blob (what the kernels stream into shared memory by TMA bulk copies).  Three parts with different
-// lifetimes inside the kernel, each starting with the same 16-byte header {np, nx, ne, nrows | ghost flag << 16}:
-//   part A  gather lists      pn u32[max_nodes]  node ids in GATHER order p (ascending id: coalesced loads of x)
-//                             xl u32[max_nx]     ids of the nodes whose coordinates are needed (affine Tet10: the
-//                                                element vertices; empty when every node needs them -> pn is used)
-//   part B  element table     et u32[(nnpe + nxr) * EP]   row k < nnpe, lane t:  p(node k) | staging entry << 16
-//                                                         rows nnpe.. (affine Tet10 only): coordinate slots, two u16 per word
+// lifetimes inside the kernel, each starting with the same 16-byte header {np, ncx | ncX << 16, ne, nrows | ghost flag << 16}:
+//   part A  gather lists      cx u32[max_ncx]    16-byte CHUNKS of the dof vector the patch reads, ascending: chunk c = doubles
+//                                                2c, 2c+1 of x (node n occupies doubles 3n..3n+2, i.e. chunks floor(3n/2) and
+//                                                floor(3n/2)+1; consecutive node ids share chunks).  One 128-bit asynchronous
+//                                                copy (LDGSTS.128) per chunk lands them back to back in the x tile.  (Runs of
+//                                                consecutive chunks as TMA bulk copies were measured slower: a structured
+//                                                mesh has ~100 runs of ~270 bytes per patch, and the bulk copies issue at
+//                                                ~40 cycles each.)
+//                             cX u32[max_ncX]    same for the coordinate array, only the nodes whose coordinates are needed
+//                                                (affine Tet10: the element vertices); empty when every node needs them:
+//                                                cx is used and the coordinate tile mirrors the x tile
+//   part B  element table     et u32[(nnpe + nxr) * EP]   row k < nnpe, lane t:  offset (in doubles) of node k in the x tile |
+//                                                         staging entry << 16;  rows nnpe.. (affine elements only): offsets of
+//                                                         the 4 geometry nodes in the coordinate tile, two u16 per word
 //   part C  reduce tables     qn u32[max_nodes]  node words in REDUCE order q (descending contribution count): interface
 //                                                flag, fixed-dof mask and the node id (interior node: the sum goes
 //                                                to y) or the partial slot of this (patch, node) (interface node)
@@ -82,7 +90,7 @@ struct DevBuf {
 // than r contributions, nodes in q order -> entry(r, q) = jo[r] + q.  The reduction reads it with consecutive lanes on
 // consecutive words; the element threads scatter into it through the precomputed entry index.
 struct PatchLayout {
-    int offA = 0, off_pn = 0, off_xl = 0;
+    int offA = 0, off_cx = 0, off_cX = 0;
     int offB = 0, off_et = 0;
     int offC = 0, off_qn = 0, off_ql = 0, off_jo = 0;
     int stride = 0;
@@ -97,7 +105,7 @@ struct PatchSetHost {
     int nnpe = 0, EP = 0;              // nodes per element, elements per patch (= element threads per block)
     int nxr = 0;                       // extra element-table rows holding coordinate slots (2 for affine Tet10, else 0)
     int64_t n_elems = 0;               // elements in this set
-    int n_patches = 0, max_nodes = 0, max_nx = 0, max_rows = 0, max_entries = 0;
+    int n_patches = 0, max_nodes = 0, max_ncx = 0, max_ncX = 0, max_rows = 0, max_entries = 0;   // max_nc*: chunks per patch
     std::vector<int64_t> elem_perm;    // internal order -> caller element index (0-based); lane t of patch p = elem_perm[p*EP+t]
     std::vector<int32_t> pnode_ptr;    // n_patches+1
     std::vector<uint32_t> qnodes;      // node words in reduce order (kept to re-embed the Dirichlet mask)
@@ -110,7 +118,7 @@ struct PatchSetHost {
 };
 
 struct PatchSetDev {
-    int cls = 0, nnpe = 0, EP = 0, nxr = 0, n_patches = 0, max_nodes = 0, max_nx = 0, max_rows = 0, max_entries = 0;
+    int cls = 0, nnpe = 0, EP = 0, nxr = 0, n_patches = 0, max_nodes = 0, max_ncx = 0, max_ncX = 0, max_rows = 0, max_entries = 0;
     int64_t n_elems = 0, elem_offset = 0;  // offset of this set in the internal element order
     PatchLayout L;
     DevBuf<uint8_t> blob;

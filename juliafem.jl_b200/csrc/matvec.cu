@@ -25,8 +25,10 @@ struct PatchKArgs {
     const uint8_t *blob;       // n_patches x stride bytes
     int n_patches, stride;
     int offB, offC, bytesA, bytesB, bytesC;   // the three parts of a blob (A starts at 0)
-    int a_pn, a_xl, b_et, c_qn, c_ql, c_jo;   // table offsets relative to their part
-    int max_nodes, max_nx, max_entries, x_all;
+    int a_cx, a_cX, b_et, c_qn, c_ql, c_jo;   // table offsets relative to their part
+    int max_nodes, max_entries, x_all;
+    int xs_cap, Xs_cap;        // doubles per x tile / coordinate tile (2 per gather chunk)
+    long long n_dofs;          // length of x / coordinates in doubles (a chunk that would read past it is copied per double)
     const double *coords;
     const double *x;
     const double *ulin;
@@ -35,7 +37,6 @@ struct PatchKArgs {
     const uint32_t *slot_node; // partial slot -> node id (only read by the non-deterministic atomic mode)
     long long elem_offset;
     int project, atomic_iface, nbuf;
-    int gmode;                 // ws kernel: 0 = look-ahead gather through registers (LDG + park), 1 = asynchronous copies (LDGSTS)
     int dbg;                   // debug_skip bits: 1 = no global stores in phase 2, 2 = no row loops, 4 = no phase 1, 8 = no look-ahead gather
     int *fail;
     const int *done;
@@ -119,32 +120,55 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// Asynchronous gather (LDGSTS) of the x / coordinate / linearisation-point entries of the patch whose part A is at pa,
-// straight into the shared tiles; no registers are held while the loads are in flight.
+// Asynchronous gather (LDGSTS.128) of the 16-byte chunks a patch reads from x (and ulin / the coordinates) straight into the
+// shared tiles; no registers are held while the copies are in flight.  Part A of the blob lists the chunks in ascending
+// order, so the tile is the concatenation of the chunks and the element table addresses it by offset.
 __device__ __forceinline__ void cp_async8(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// the executing thread's prior cp.async operations arrive on the mbarrier when they have landed (count pre-charged: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-template <int T, int NF>
-__device__ __forceinline__ void patch_gather_async(const PatchKArgs &a, const unsigned char *pa, int tid, double *xs, double *Xs, double *us) {
-    const int *hdr = reinterpret_cast<const int *>(pa);
-    const int np = hdr[0], nx = hdr[1];
-    const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
-    const uint32_t *xl = reinterpret_cast<const uint32_t *>(pa + a.a_xl);
-    for (int j = tid; j < np; j += T) {   // one node (3 x 8-byte copies) per thread: few instructions per copy
-        const long long g = 3 * (long long)pn[j];
-        cp_async8(xs + 3 * j, a.x + g); cp_async8(xs + 3 * j + 1, a.x + g + 1); cp_async8(xs + 3 * j + 2, a.x + g + 2);
-        if (NF == 2) { cp_async8(us + 3 * j, a.ulin + g); cp_async8(us + 3 * j + 1, a.ulin + g + 1); cp_async8(us + 3 * j + 2, a.ulin + g + 2); }
-        if (a.x_all) { cp_async8(Xs + 3 * j, a.coords + g); cp_async8(Xs + 3 * j + 1, a.coords + g + 1); cp_async8(Xs + 3 * j + 2, a.coords + g + 2); }
-    }
-    if (!a.x_all)
-        for (int j = tid; j < nx; j += T) {
-            const long long g = 3 * (long long)xl[j];
-            cp_async8(Xs + 3 * j, a.coords + g); cp_async8(Xs + 3 * j + 1, a.coords + g + 1); cp_async8(Xs + 3 * j + 2, a.coords + g + 2);
+// Gather the chunks j = tid, tid + nthr, ... of a chunk list into `tile` (chunk c = doubles 2c, 2c+1): src = dof vector (or
+// coordinates) of n_tot doubles, of which the first n_own are read from src itself by one 128-bit asynchronous copy per
+// chunk; a chunk that ends beyond n_own is copied per double: doubles n_own..n_tot-1 (ghost values of a partitioned mesh,
+// fused halo) come from the landing buffer `land` the neighbours wrote (volatile: the same addresses are rewritten every
+// second exchange, no stale L1 line).  Returns true if this thread wrote the tile with ordinary stores.
+__device__ __forceinline__ bool gather_chunks(const uint32_t *ch, int n, int tid, int nthr, double *tile, const double *src, long long n_own,
+                                              long long n_tot, const double *land) {
+    bool plain = false;
+    for (int j = tid; j < n; j += nthr) {
+        const long long d = 2LL * ch[j];
+        if (d + 2 <= n_own) cp_async16(tile + 2 * j, src + d);
+        else {
+            JF_UNROLL for (int e = 0; e < 2; e++) {
+                if (d + e < n_own) cp_async8(tile + 2 * j + e, src + d + e);
+                else if (d + e < n_tot && land) { tile[2 * j + e] = __ldcv(land + (d + e - n_own)); plain = true; }
+            }
         }
-    cp_async_commit();
+    }
+    return plain;
+}
+
+// All T threads of a block: issue the gather of the patch whose part A is at pa and arrive on `bar` (count T).
+template <int T, int NF>
+__device__ __forceinline__ void patch_gather_async(const PatchKArgs &a, const unsigned char *pa, int tid, double *xs, double *Xs, double *us, uint64_t *bar) {
+    const int *hdr = reinterpret_cast<const int *>(pa);
+    const int ncx = hdr[1] & 0xFFFF, ncX = hdr[1] >> 16;
+    const uint32_t *cx = reinterpret_cast<const uint32_t *>(pa + a.a_cx);
+    const uint32_t *cX = reinterpret_cast<const uint32_t *>(pa + a.a_cX);
+    gather_chunks(cx, ncx, tid, T, xs, a.x, a.n_dofs, a.n_dofs, nullptr);
+    if (NF == 2) gather_chunks(cx, ncx, tid, T, us, a.ulin, a.n_dofs, a.n_dofs, nullptr);
+    if (a.x_all) gather_chunks(cx, ncx, tid, T, Xs, a.coords, a.n_dofs, a.n_dofs, nullptr);
+    else gather_chunks(cX, ncX, tid, T, Xs, a.coords, a.n_dofs, a.n_dofs, nullptr);
+    cp_async_mbar_arrive(bar);
 }
 
 // ---- phase 2 of one patch by NT threads (t = 0..NT-1): ten nodes per warp, lane = 3 * node + component.
@@ -184,78 +208,74 @@ __device__ __forceinline__ void reduce_patch(const PatchKArgs &a, const unsigned
     }
 }
 
-// ---- phase 2 for the warp-specialised kernel: same mapping (ten nodes per warp, lane = 3 * node + component), but every
-// thread owns up to MC nodes (q, q + 10 NW, q + 20 NW, ...) and walks the staging rows ONCE for all of them.  With two
-// helper warps per scheduler the code is latency-bound, so it is written branch-free: warp-uniform loop bounds
-// (redux.sync max), MC independent load/add chains per thread.
-template <int NW, int MC>
-__device__ __forceinline__ void reduce_patch_ilp(const PatchKArgs &a, const unsigned char *pc, const double *stage, const double *zero, int t, long long *tm = nullptr) {
-    const int np = reinterpret_cast<const int *>(pc)[0];
+// ---- phase 2 for the warp-specialised kernel, "flat" form.  The staging tile is read as rows of 3 * rowlen[r] consecutive
+// doubles (component-interleaved, nodes in reduce order q); flat index i = 3 q + c.  Thread t of the NT helper threads owns
+// the flat indices t, t + NT, t + 2 NT, ... (MC accumulators, "chains") and adds row after row: consecutive lanes read
+// consecutive words (conflict-free, all 32 lanes busy).  The row lengths are non-increasing (nodes sorted by descending
+// contribution count), so the rows in which a warp has more than MC/2, more than MC/4 or at least one chain are three
+// contiguous blocks: their bounds come from one ballot each over row descriptors held one per lane, and each block is a
+// counted loop over predicated loads with no data-dependent branch inside (the descriptors travel by shuffle, not through
+// memory), unrolled so that several rows are in flight.  Summation order per (node, component): rows ascending -- fixed,
+// no atomics, bitwise reproducible.
+// rows [r, r_end) of the current block of 32 row descriptors, C predicated chains, U rows in flight
+template <int NT, int C, int U>
+__device__ __forceinline__ void flat_rows(const double *sp, unsigned desc, int &r, int r_end, int rb, int base, int t, double *acc) {
+#pragma unroll U
+    for (; r < r_end; r++) {
+        const unsigned d = __shfl_sync(0xFFFFFFFFu, desc, r - rb);
+        const double *row = sp + 3 * (int)(d & 0xFFFFu);
+        const int l3 = (int)(d >> 16) - base;
+        JF_UNROLL for (int m = 0; m < C; m++)
+            if (t + NT * m < l3) acc[m] += row[NT * m];
+    }
+}
+
+template <int NT, int MC>
+__device__ __forceinline__ void reduce_patch_flat(const PatchKArgs &a, const unsigned char *pc, const double *stage, int t, long long *tm = nullptr) {
+    const int *hdr = reinterpret_cast<const int *>(pc);
+    const int np = hdr[0], nrows = (a.dbg & 2) ? 0 : (hdr[3] & 0xFFFF), n3 = 3 * np;
     const uint32_t *qn = reinterpret_cast<const uint32_t *>(pc + a.c_qn);
-    const uint8_t *ql = pc + a.c_ql;
     const uint16_t *jo = reinterpret_cast<const uint16_t *>(pc + a.c_jo);
-    const int warp = t >> 5, lane = t & 31;
-    const int sub = lane / 3, c = lane - 3 * sub;
-    const unsigned full = 0xFFFFFFFFu;
-    constexpr int QS = 10 * NW;   // node stride between a thread's chains
-    for (int q0 = 0; q0 < np; q0 += QS * MC) {   // one pass unless the patch has more than QS * MC nodes
-        const int q = q0 + warp * 10 + sub;
-        int len[MC];
-        double sum[MC];
-        JF_UNROLL for (int m = 0; m < MC; m++) {
-            const int qm = q + QS * m;
-            len[m] = (sub < 10 && qm < np) ? (int)ql[qm] : 0;
-            sum[m] = 0.0;
-        }
+    const int lane = t & 31, wf = t & ~31;   // wf = first flat index of this warp inside a block of NT
+    for (int base = 0; base < n3; base += NT * MC) {   // one pass unless the patch has more than NT * MC / 3 nodes
+        double acc[MC];
+        JF_UNROLL for (int m = 0; m < MC; m++) acc[m] = 0.0;
+        const double *sp = stage + base + t;
         if (tm) tm[3] = clock64();
-        const double *sp = stage + 3 * q + c;
-        int r = 0;
-        // rows r < len[m] belong to chain m; a finished chain reads the zero word instead (address select, no predicated
-        // loads: predicates are scarce and serialise the chains).  Loop bounds are warp-uniform maxima; the chain set
-        // shrinks in four steps (lens are sorted: len[0] >= len[1] >= ...).
-        // warp-uniform loop bounds: lane 0 holds the warp's first node of every chain, i.e. (sorted order) the longest
-        const unsigned lens4 = __shfl_sync(full, (unsigned)len[5] | ((unsigned)len[2] << 8) | ((unsigned)len[1] << 16) | ((unsigned)len[0] << 24), 0);
-        auto rows = [&](auto nchain, auto unroll, int lim) {
-            constexpr int NC = decltype(nchain)::value, UN = decltype(unroll)::value;
-            if (a.dbg & 2) lim = 0;
-#pragma unroll UN
-            for (; r < lim; r++) {
-                const double *row = sp + 3 * jo[r];
-                JF_UNROLL for (int m = 0; m < NC; m++) {
-                    const double *src = (r < len[m]) ? row + 3 * QS * m : zero;
-                    sum[m] += *src;
-                }
+        for (int rb = 0; rb < nrows; rb += 32) {         // row descriptors, one per lane: offset | flat length << 16
+            unsigned desc = 0;
+            if (rb + lane < nrows) {
+                const unsigned o = jo[rb + lane];
+                desc = o | ((3u * ((unsigned)jo[rb + lane + 1] - o)) << 16);
             }
-        };
-        using std::integral_constant;
-        static_assert(MC >= 6, "chain steps assume at least six chains");
-        rows(integral_constant<int, MC>(), integral_constant<int, 2>(), (int)(lens4 & 255u));          // until chains 5.. are complete
-        rows(integral_constant<int, 5>(), integral_constant<int, 2>(), (int)((lens4 >> 8) & 255u));    // until chains 2..4 are complete
-        rows(integral_constant<int, 2>(), integral_constant<int, 4>(), (int)((lens4 >> 16) & 255u));
-        rows(integral_constant<int, 1>(), integral_constant<int, 8>(), (int)(lens4 >> 24));
-        if (tm) { tm[4] = clock64(); tm[6] = r; }
+            const int l3 = (int)(desc >> 16) - base - wf;   // flat entries of my row from this warp's first index on
+            // row blocks by the number of chains this warp has in them (non-increasing): > MC/2, > MC/4, >= 1
+            const int R8 = rb + __popc(__ballot_sync(0xFFFFFFFFu, l3 > NT * (MC / 2)));
+            const int R4 = rb + __popc(__ballot_sync(0xFFFFFFFFu, l3 > NT * (MC / 4)));
+            const int R2 = rb + __popc(__ballot_sync(0xFFFFFFFFu, l3 > 0));
+            int r = rb;
+            flat_rows<NT, MC, 2>(sp, desc, r, R8, rb, base, t, acc);
+            flat_rows<NT, MC / 2, 2>(sp, desc, r, R4, rb, base, t, acc);
+            flat_rows<NT, MC / 4, 4>(sp, desc, r, R2, rb, base, t, acc);
+        }
+        if (tm) { tm[4] = clock64(); tm[6] = nrows; }
         if (a.dbg & 1) continue;
-        // stores, branch-free: all table lookups first, then one (predicated) store per chain
+        // stores: all table lookups first, then one predicated store per chain
         uint32_t w[MC];
         JF_UNROLL for (int m = 0; m < MC; m++) {
-            const int qm = q + QS * m;
-            w[m] = qn[(sub < 10 && qm < np) ? qm : 0];
+            const int i = base + t + NT * m;
+            w[m] = qn[i < n3 ? (int)(((unsigned)i * 43691u) >> 17) : 0];   // i / 3 for i < 98 304
         }
-        if (!a.atomic_iface) {
-            JF_UNROLL for (int m = 0; m < MC; m++) {
-                double v = sum[m];
-                if (a.project && ((w[m] >> (PN_FIXSHIFT + c)) & 1u)) v = 0.0;
-                double *base = (w[m] & PN_IFACE) ? a.ipart : a.y;   // interface node: its partial slot of this patch
-                if (sub < 10 && q + QS * m < np) base[3 * (long long)(w[m] & PN_ID_MASK) + c] = v;
-            }
-        } else {
-            JF_UNROLL for (int m = 0; m < MC; m++) {
-                const bool ok = sub < 10 && q + QS * m < np;
-                double v = sum[m];
-                if (a.project && ((w[m] >> (PN_FIXSHIFT + c)) & 1u)) v = 0.0;
-                const long long id = w[m] & PN_ID_MASK;
-                if (ok && (w[m] & PN_IFACE)) atomicAdd(a.y + 3 * (long long)a.slot_node[id] + c, v);
-                else if (ok) a.y[3 * id + c] = v;
+        JF_UNROLL for (int m = 0; m < MC; m++) {
+            const int i = base + t + NT * m;
+            const int c = i - 3 * (int)(((unsigned)i * 43691u) >> 17);
+            double v = acc[m];
+            if (a.project && ((w[m] >> (PN_FIXSHIFT + c)) & 1u)) v = 0.0;
+            const long long id = w[m] & PN_ID_MASK;
+            if (i < n3) {
+                if (!(w[m] & PN_IFACE)) a.y[3 * id + c] = v;
+                else if (!a.atomic_iface) a.ipart[3 * id + c] = v;   // interface node: its partial slot of this patch
+                else atomicAdd(a.y + 3 * (long long)a.slot_node[id] + c, v);
             }
         }
     }
@@ -276,16 +296,17 @@ __global__ void __launch_bounds__(T, 1) patch_kernel(PatchKArgs a, Pt pt) {
     constexpr int NF = Pt::NF;
     const int tid = threadIdx.x;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smraw);
-    unsigned char *blob0 = smraw + 16;
-    double *stage = reinterpret_cast<double *>(smraw + 16 + a.nbuf * (size_t)a.stride);
+    unsigned char *blob0 = smraw + 32;
+    double *stage = reinterpret_cast<double *>(smraw + 32 + a.nbuf * (size_t)a.stride);
     double *xs = stage + 3 * a.max_entries;
-    double *Xs = xs + 3 * a.max_nodes;
-    double *us = Xs + 3 * (a.x_all ? a.max_nodes : a.max_nx);
+    double *Xs = xs + a.xs_cap;
+    double *us = Xs + a.Xs_cap;
     const int stride_p = gridDim.x;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], T);   // x / coordinate tiles of the next patch have landed
         mbar_fence_init();
     }
     __syncthreads();
@@ -296,14 +317,14 @@ __global__ void __launch_bounds__(T, 1) patch_kernel(PatchKArgs a, Pt pt) {
     }
     if (p < a.n_patches) {
         mbar_wait(&mbar[0], 0);
-        patch_gather_async<T, NF>(a, blob0, tid, xs, Xs, us);
+        patch_gather_async<T, NF>(a, blob0, tid, xs, Xs, us, &mbar[2]);
     }
     for (int it = 0; p < a.n_patches; it++, p += stride_p) {
         const int buf = a.nbuf == 2 ? (it & 1) : 0;
         const unsigned char *bl = blob0 + (size_t)buf * a.stride;
         const int ne = reinterpret_cast<const int *>(bl)[2];
         // ---- (a) the asynchronous gather of this patch (issued during the previous patch's phase 2) must have landed
-        cp_async_wait_all();
+        mbar_wait(&mbar[2], it & 1);
         __syncthreads();
         // ---- (b) every thread has left phase 2 of the previous patch: its blob buffer may be refilled
         const bool has_next = p + stride_p < a.n_patches;
@@ -321,7 +342,7 @@ __global__ void __launch_bounds__(T, 1) patch_kernel(PatchKArgs a, Pt pt) {
         // ---- (d) start the next patch's gather (its blob was requested at (b))
         if (has_next && a.nbuf == 2) {
             mbar_wait(&mbar[buf ^ 1], ((it + 1) >> 1) & 1);
-            patch_gather_async<T, NF>(a, blob0 + (size_t)(buf ^ 1) * a.stride, tid, xs, Xs, us);
+            patch_gather_async<T, NF>(a, blob0 + (size_t)(buf ^ 1) * a.stride, tid, xs, Xs, us, &mbar[2]);
         }
         // ---- (e) phase 2 (the in-flight gather writes only xs/Xs/us, which phase 2 does not read)
         reduce_patch<T>(a, bl + a.offC, stage, tid);
@@ -333,45 +354,47 @@ __global__ void __launch_bounds__(T, 1) patch_kernel(PatchKArgs a, Pt pt) {
                 bulk_g2s(blob0, a.blob + (size_t)(p + stride_p) * a.stride, a.stride, &mbar[0]);
             }
             mbar_wait(&mbar[0], (it + 1) & 1);
-            patch_gather_async<T, NF>(a, blob0, tid, xs, Xs, us);
+            patch_gather_async<T, NF>(a, blob0, tid, xs, Xs, us, &mbar[2]);
         }
     }
     if (a.tail) iface_tail(a);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Warp-specialised variant (linear-elastic operators): one persistent block per SM with
-//   * 8 COMPUTE warps (256 threads, registers raised with setmaxnreg): look-ahead gather of patch i+1 into registers,
-//     phase 1 of patch i, park the registers in the other x tile
-//   * 8 HELPER warps (256 threads, registers lowered): phase 2 of patch i-1 concurrently with the compute warps
-// so the fp64 pipe never waits for the reduction / store phase.  Hand-off through mbarrier full/empty pairs on a double
-// buffered staging tile; the three blob parts are double buffered separately (they are live at different times) and
-// refilled by TMA bulk copies from the role that consumes them.
+// Warp-specialised variant (linear-elastic operators on affine elements): one persistent block per SM with two roles
+//   * 8 COMPUTE warps (256 threads, registers raised with setmaxnreg): phase 1 of patch i and nothing else.  No barrier
+//     between the compute warps: they wait on mbarriers only and drift apart freely (two warps in lockstep on one
+//     scheduler stall together on the shared fp64 pipe: 64 % vs 75 % pipe utilisation in isolation,
+//     profiles/microbench/phase1_occupancy.cu)
+//   * 8 HELPER warps (256 threads, registers lowered): for patch k, first the look-ahead gather of patch k+2 -- 128-bit
+//     asynchronous copies (LDGSTS.128) of the 16-byte chunks of x and of the coordinate array listed in part A of the
+//     blob, straight into the x tile patch k has just released; completion is signalled on an mbarrier by
+//     cp.async.mbarrier.arrive, nobody waits on the loads -- then phase 2 of patch k, concurrently with phase 1 of patch
+//     k+1.  They also request the blob parts (TMA bulk copies) and, on partitioned meshes, carry the halo exchange.
+// Hand-off through mbarrier full/empty pairs on double-buffered x tiles and staging tiles; the three blob parts are
+// double buffered separately (they are live at different times).
 // ------------------------------------------------------------------------------------------------------------------
-#define WS_T 256
-#define WS_H 256
+#define WS_T 256            // compute threads = elements per patch
+#define WS_H 256            // helper threads
 #define WS_COMPUTE_REGS 168 // 256*168 + 256*88 = 512*128: setmaxnreg redistributes the launch allocation, it cannot grow it
 #define WS_HELPER_REGS 88
-#define WS_GN 3             // nodes per compute thread held in registers by the look-ahead gather (768 nodes)
-#define WS_MC 10            // nodes per helper thread reduced concurrently (8 warps x 10 nodes x 10 = 800 nodes per pass)
+#define WS_MC 8             // flat indices per helper thread and pass (256 x 8 = 2 048 >= 3 x 682 nodes)
 
 struct WsSmem {   // byte offsets inside dynamic shared memory, computed on the host
     int A, B, C, stage, xs, Xs, total;
     int strideA, strideB, strideC;
 };
 
-template <int NNPE, int CLS, int MODE, class Pt, int GC>
+template <int NNPE, int CLS, int MODE, class Pt>
 __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, Pt pt, WsSmem L) {
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr int T = WS_T;
     uint64_t *mb = reinterpret_cast<uint64_t *>(sm);
-    uint64_t *A_full = mb, *B_full = mb + 2, *C_full = mb + 4, *stage_full = mb + 6, *stage_empty = mb + 8;
-    double *zero3 = reinterpret_cast<double *>(sm + 96);   // a zero word for the finished chains of the reduction
+    uint64_t *A_full = mb, *B_full = mb + 2, *C_full = mb + 4, *stage_full = mb + 6, *stage_empty = mb + 8, *x_full = mb + 10;
     const size_t stage_sz = 3 * (size_t)a.max_entries;
     double *stage0 = reinterpret_cast<double *>(sm + L.stage);
     double *xs0 = reinterpret_cast<double *>(sm + L.xs);
     double *Xs0 = reinterpret_cast<double *>(sm + L.Xs);
-    const int xs_sz = 3 * a.max_nodes, Xs_sz = 3 * (a.x_all ? a.max_nodes : a.max_nx);
     const int n_it = (a.n_patches - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto patch_of = [&](int i) { return (size_t)(blockIdx.x + (size_t)i * gridDim.x); };
     auto reqA = [&](int i) {
@@ -389,16 +412,13 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
 
     if (threadIdx.x == 0) {
         for (int k = 0; k < 6; k++) mbar_init(&mb[k], 1);
-        for (int k = 0; k < 2; k++) { mbar_init(&stage_full[k], WS_T); mbar_init(&stage_empty[k], WS_H); }
+        for (int k = 0; k < 2; k++) { mbar_init(&stage_full[k], WS_T); mbar_init(&stage_empty[k], WS_H); mbar_init(&x_full[k], WS_H); }
         mbar_fence_init();
-        zero3[0] = 0.0;
-        for (int k = 0; k < 2 && k < n_it; k++) { reqA(k); reqC(k); }
-        if (n_it > 0) reqB(0);
+        for (int k = 0; k < 2 && k < n_it; k++) { reqA(k); reqB(k); reqC(k); }
     }
     __syncthreads();
     if (a.done && *a.done) {   // device-side convergence flag of the CG loop: nothing to do; let the requested copies land first
-        for (int k = 0; k < 2 && k < n_it; k++) { mbar_wait(&A_full[k], 0); mbar_wait(&C_full[k], 0); }
-        if (n_it > 0) mbar_wait(&B_full[0], 0);
+        for (int k = 0; k < 2 && k < n_it; k++) { mbar_wait(&A_full[k], 0); mbar_wait(&B_full[k], 0); mbar_wait(&C_full[k], 0); }
         if (a.tail && threadIdx.x == 0) atomicAdd(a.gbar, 1u);
         return;
     }
@@ -407,143 +427,26 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         // =========================== compute warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_COMPUTE_REGS));
         const int tid = threadIdx.x;
-        // look-ahead gather registers: thread t holds the 3 components of nodes t, t + T, t + 2T (one index lookup and one
-        // address per node; the three 8-byte loads of a node hit the same sectors)
-        double rx[WS_GN][3], rc[GC][3];
-        JF_UNROLL for (int r = 0; r < WS_GN; r++) rx[r][0] = rx[r][1] = rx[r][2] = 0.0;
-        JF_UNROLL for (int r = 0; r < GC; r++) rc[r][0] = rc[r][1] = rc[r][2] = 0.0;
-        bool halo_seen = !a.halo;
-        // value of node id: owned nodes from x; ghost nodes from the landing buffer the neighbours wrote (volatile: the
-        // same addresses are rewritten every second exchange, so the read must not hit a stale L1 line)
-        auto node_ptr = [&](uint32_t id, bool &ghost) -> const double * {
-            ghost = id >= a.n_owned;
-            return ghost ? a.hf.land + 3 * (long long)(id - a.n_owned) : a.x + 3 * (long long)id;
-        };
-        auto load_regs = [&](const unsigned char *pa) {
-            const int *hdr = reinterpret_cast<const int *>(pa);
-            const int np = (a.dbg & 8) ? 0 : hdr[0], nx = (a.dbg & 8) ? 0 : (a.x_all ? np : hdr[1]);
-            if (!halo_seen && (hdr[3] & 0x10000)) {   // first patch that reads ghost values: the neighbours' data must have landed
-                if (tid < a.hf.n_nb) {
-                    const volatile unsigned long long *f = a.hf.my_flag[tid];
-                    while (*f < a.hf.seq) { }
-                    __threadfence_system();   // acquire side: only the polling threads fence; the barrier extends it to the block
-                }
-                named_sync(3, WS_T);
-                halo_seen = true;
-            }
-            const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
-            const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
-            JF_UNROLL for (int r = 0; r < WS_GN; r++) {
-                const int j = tid + r * T;
-                bool ghost;
-                const double *g = node_ptr(pn[j < np ? j : 0], ghost);
-                if (ghost) { rx[r][0] = __ldcv(g); rx[r][1] = __ldcv(g + 1); rx[r][2] = __ldcv(g + 2); }
-                else { rx[r][0] = __ldg(g); rx[r][1] = __ldg(g + 1); rx[r][2] = __ldg(g + 2); }
-            }
-            JF_UNROLL for (int r = 0; r < GC; r++) {
-                const int j = tid + r * T;
-                const double *g = a.coords + 3 * (long long)xl[j < nx ? j : 0];
-                rc[r][0] = __ldg(g); rc[r][1] = __ldg(g + 1); rc[r][2] = __ldg(g + 2);
-            }
-        };
-        // registers -> shared tiles (+ slow paths for patches with more nodes than the registers hold)
-        auto store_regs = [&](const unsigned char *pa, double *xs, double *Xs) {
-            const int *hdr = reinterpret_cast<const int *>(pa);
-            const int np = hdr[0], nx = a.x_all ? np : hdr[1];
-            JF_UNROLL for (int r = 0; r < WS_GN; r++) {
-                const int j = tid + r * T;
-                if (j < np) { xs[3 * j] = rx[r][0]; xs[3 * j + 1] = rx[r][1]; xs[3 * j + 2] = rx[r][2]; }
-            }
-            JF_UNROLL for (int r = 0; r < GC; r++) {
-                const int j = tid + r * T;
-                if (j < nx) { Xs[3 * j] = rc[r][0]; Xs[3 * j + 1] = rc[r][1]; Xs[3 * j + 2] = rc[r][2]; }
-            }
-            const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
-            const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
-            for (int j = tid + WS_GN * T; j < np; j += T) {
-                bool ghost;
-                const double *g = node_ptr(pn[j], ghost);
-                if (ghost) { xs[3 * j] = __ldcv(g); xs[3 * j + 1] = __ldcv(g + 1); xs[3 * j + 2] = __ldcv(g + 2); }
-                else { xs[3 * j] = __ldg(g); xs[3 * j + 1] = __ldg(g + 1); xs[3 * j + 2] = __ldg(g + 2); }
-            }
-            for (int j = tid + GC * T; j < nx; j += T) {
-                const double *g = a.coords + 3 * (long long)xl[j];
-                Xs[3 * j] = __ldg(g); Xs[3 * j + 1] = __ldg(g + 1); Xs[3 * j + 2] = __ldg(g + 2);
-            }
-        };
-        // alternative look-ahead gather (a.gmode = 1): asynchronous copies (LDGSTS) straight into the other tiles -- no
-        // registers, no parking pass; ghost values (rare) are read synchronously from the landing buffer
-        auto gather_async = [&](const unsigned char *pa, double *xs, double *Xs) {
-            const int *hdr = reinterpret_cast<const int *>(pa);
-            const int np = hdr[0], nx = a.x_all ? np : hdr[1];
-            if (!halo_seen && (hdr[3] & 0x10000)) {
-                if (tid < a.hf.n_nb) {
-                    const volatile unsigned long long *f = a.hf.my_flag[tid];
-                    while (*f < a.hf.seq) { }
-                    __threadfence_system();   // acquire side: only the polling threads fence; the barrier extends it to the block
-                }
-                named_sync(3, WS_T);
-                halo_seen = true;
-            }
-            const uint32_t *pn = reinterpret_cast<const uint32_t *>(pa + a.a_pn);
-            const uint32_t *xl = a.x_all ? pn : reinterpret_cast<const uint32_t *>(pa + a.a_xl);
-            for (int j = tid; j < np; j += T) {   // one node per lane and step (a flat item-per-lane mapping touches a third of
-                bool ghost;                       // the sectors but was measured slower: 2 500 instead of 1 450 issue cycles)
-                const double *g = node_ptr(pn[j], ghost);
-                double *d = xs + 3 * j;
-                if (ghost) { d[0] = __ldcv(g); d[1] = __ldcv(g + 1); d[2] = __ldcv(g + 2); }
-                else { cp_async8(d, g); cp_async8(d + 1, g + 1); cp_async8(d + 2, g + 2); }
-            }
-            for (int j = tid; j < nx; j += T) {
-                const double *g = a.coords + 3 * (long long)xl[j];
-                double *d = Xs + 3 * j;
-                cp_async8(d, g); cp_async8(d + 1, g + 1); cp_async8(d + 2, g + 2);
-            }
-            cp_async_commit();
-        };
-        if (n_it > 0) {
-            mbar_wait(&A_full[0], 0);
-            if (a.gmode) { gather_async(sm + L.A, xs0, Xs0); cp_async_wait_all(); }
-            else { load_regs(sm + L.A); store_regs(sm + L.A, xs0, Xs0); }
-            named_sync(2, WS_T);
-        }
         for (int i = 0; i < n_it; i++) {
-            const bool has_next = i + 1 < n_it;
+            const int b = i & 1;
             const bool tm = a.timing && blockIdx.x == 0 && tid == 0 && i < 8;
             if (tm) a.timing[i * 8 + 0] = clock64();
-            const unsigned char *pan = sm + L.A + (size_t)((i + 1) & 1) * L.strideA;
-            if (has_next) {
-                mbar_wait(&A_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-                if (tm) a.timing[i * 8 + 5] = clock64();
-                if (a.gmode) gather_async(pan, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
-                else load_regs(pan);
-            }
-            // part A of patch i and part B of patch i-1 are dead (barrier at the end of the previous iteration): refill
-            if (tid == WS_T - 32) {
-                if (i + 2 < n_it) reqA(i + 2);
-                if (has_next) reqB(i + 1);
-            }
+            mbar_wait(&x_full[b], (i >> 1) & 1);
+            mbar_wait(&B_full[b], (i >> 1) & 1);
             if (tm) a.timing[i * 8 + 1] = clock64();
-            if (i >= 2) mbar_wait(&stage_empty[i & 1], ((i >> 1) - 1) & 1);
-            mbar_wait(&B_full[i & 1], (i >> 1) & 1);
+            if (i >= 2) mbar_wait(&stage_empty[b], ((i >> 1) - 1) & 1);
             if (tm) a.timing[i * 8 + 2] = clock64();
-            const unsigned char *pb = sm + L.B + (size_t)(i & 1) * L.strideB;
+            const unsigned char *pb = sm + L.B + (size_t)b * L.strideB;
             const int ne = reinterpret_cast<const int *>(pb)[2];
             if (tid < ne && !(a.dbg & 4)) {
                 const uint32_t *et = reinterpret_cast<const uint32_t *>(pb + a.b_et);
                 const bool ok = element_phase<NNPE, CLS, MODE, Pt, T>(pt, a.elem_offset + (long long)patch_of(i) * T + tid, et, tid,
-                                                                      xs0 + (size_t)(i & 1) * xs_sz, Xs0 + (size_t)(i & 1) * Xs_sz, nullptr,
-                                                                      stage0 + (size_t)(i & 1) * stage_sz);
+                                                                      xs0 + (size_t)b * a.xs_cap, Xs0 + (size_t)b * a.Xs_cap, nullptr,
+                                                                      stage0 + (size_t)b * stage_sz);
                 if (!ok) atomicOr(a.fail, 1);
             }
             if (tm) a.timing[i * 8 + 3] = clock64();
-            mbar_arrive(&stage_full[i & 1]);
-            if (has_next) {
-                if (a.gmode) cp_async_wait_all();
-                else store_regs(pan, xs0 + (size_t)((i + 1) & 1) * xs_sz, Xs0 + (size_t)((i + 1) & 1) * Xs_sz);
-                named_sync(2, WS_T);   // tile (i+1)&1 complete and visible to every compute warp
-            }
-            if (tm) a.timing[i * 8 + 4] = clock64();
+            mbar_arrive(&stage_full[b]);   // release: this thread's staging stores; x tile b and part B slot b are free, too
         }
     } else {
         // =========================== helper warps ===========================
@@ -551,7 +454,7 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
         const int hid = threadIdx.x - WS_T;
         if (a.halo) {
             // push this rank's interface values into the neighbours' landing buffers (all helper threads of all blocks),
-            // fence, and let the last block to finish publish the sequence flags -- while the compute warps fill the pipeline
+            // fence, and let the last block to finish publish the sequence flags -- while the pipeline fills
             const long long n3 = 3 * a.hf.send_off[a.hf.n_nb];
             for (long long i = (long long)blockIdx.x * WS_H + hid; i < n3; i += (long long)gridDim.x * WS_H) {
                 const long long q = i / 3;
@@ -560,8 +463,7 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 a.hf.peer_land[nb][i - 3 * a.hf.send_off[nb]] = a.x[3LL * a.hf.send_nodes[q] + (i - 3 * q)];
             }
             // one system-scope fence per block, by the thread that takes the ticket (the barrier orders the other threads'
-            // remote stores before it; fence cumulativity makes them visible before the flag).  A fence in every thread
-            // costs one MEMBAR.SYS per warp, and its latency grows with the number of mapped peers (8 GPUs: +40 us per step).
+            // remote stores before it; fence cumulativity makes them visible before the flag).
             named_sync(1, WS_H);
             if (hid == 0) {
                 __threadfence_system();
@@ -573,21 +475,61 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
                 }
             }
         }
+        bool halo_seen = !a.halo;
+        const long long n_own3 = a.halo ? 3LL * a.n_owned : a.n_dofs;   // doubles of x that are this rank's own
+        // look-ahead gather of patch j into x tile j & 1 (part A slot j & 1 holds its chunk lists)
+        auto gather = [&](int j) {
+            const int b = j & 1;
+            mbar_wait(&A_full[b], (j >> 1) & 1);
+            const unsigned char *pa = sm + L.A + (size_t)b * L.strideA;
+            const int *hdr = reinterpret_cast<const int *>(pa);
+            const int ncx = (a.dbg & 8) ? 0 : (hdr[1] & 0xFFFF), ncX = (a.dbg & 8) ? 0 : (hdr[1] >> 16);
+            if (!halo_seen && (hdr[3] & 0x10000)) {   // first patch that reads ghost values: the neighbours' data must have landed
+                if (hid < a.hf.n_nb) {
+                    const volatile unsigned long long *f = a.hf.my_flag[hid];
+                    while (*f < a.hf.seq) { }
+                    __threadfence_system();   // acquire side: only the polling threads fence; the barrier extends it to the block
+                }
+                named_sync(1, WS_H);
+                halo_seen = true;
+            }
+            const uint32_t *cx = reinterpret_cast<const uint32_t *>(pa + a.a_cx);
+            const uint32_t *cX = reinterpret_cast<const uint32_t *>(pa + a.a_cX);
+            double *xs = xs0 + (size_t)b * a.xs_cap, *Xs = Xs0 + (size_t)b * a.Xs_cap;
+            const bool plain = gather_chunks(cx, ncx, hid, WS_H, xs, a.x, n_own3, a.n_dofs, a.halo ? a.hf.land : nullptr);
+            if (a.x_all) gather_chunks(cx, ncx, hid, WS_H, Xs, a.coords, a.n_dofs, a.n_dofs, nullptr);
+            else gather_chunks(cX, ncX, hid, WS_H, Xs, a.coords, a.n_dofs, a.n_dofs, nullptr);
+            if (plain) __threadfence_block();
+            cp_async_mbar_arrive(&x_full[b]);
+        };
+        for (int j = 0; j < 2 && j < n_it; j++) gather(j);
+        if (n_it > 2) {
+            named_sync(1, WS_H);   // every helper thread has read the chunk lists of patches 0 and 1
+            if (hid == 0) { reqA(2); if (n_it > 3) reqA(3); }
+        }
         for (int k = 0; k < n_it; k++) {
             const bool tm = a.timing && blockIdx.x == 0 && hid == 0 && k < 8;
             if (tm) a.timing[64 + k * 8 + 0] = clock64();
             mbar_wait(&C_full[k & 1], (k >> 1) & 1);
             mbar_wait(&stage_full[k & 1], (k >> 1) & 1);
             if (tm) a.timing[64 + k * 8 + 1] = clock64();
-            reduce_patch_ilp<WS_H / 32, WS_MC>(a, sm + L.C + (size_t)(k & 1) * L.strideC, stage0 + (size_t)(k & 1) * stage_sz, zero3, hid, tm ? a.timing + 64 + k * 8 : nullptr);
+            // every compute thread is past phase 1 of patch k: x tile and part B slot k & 1 are free -> patch k + 2
+            if (k + 2 < n_it) {
+                if (hid == 0) reqB(k + 2);
+                gather(k + 2);
+            }
+            if (tm) a.timing[64 + k * 8 + 5] = clock64();
+            reduce_patch_flat<WS_H, WS_MC>(a, sm + L.C + (size_t)(k & 1) * L.strideC, stage0 + (size_t)(k & 1) * stage_sz, hid, tm ? a.timing + 64 + k * 8 : nullptr);
             if (tm) a.timing[64 + k * 8 + 2] = clock64();
             mbar_arrive(&stage_empty[k & 1]);
-            // part C slot (k & 1) is free once every helper thread is past the reduction: refill it with patch k + 2
+            // part C slot (k & 1) is free once every helper thread is past the reduction, part A slot (k & 1) once every
+            // helper thread has issued the gather of patch k + 2: refill them with patches k + 2 / k + 4
             if (k + 2 < n_it) {
                 named_sync(1, WS_H);
-                if (hid == 0) reqC(k + 2);
+                if (hid == 0) { reqC(k + 2); if (k + 4 < n_it) reqA(k + 4); }
             }
         }
+        cp_async_wait_all();   // nothing may still be in flight into shared memory when the block exits
     }
     if (a.tail) iface_tail(a);
 }
@@ -663,7 +605,7 @@ int ensure_built(jfem_handle *h) {
         PatchSetHost &S = h->hsets[c];
         PatchSetDev &D = h->dsets[c];
         D.release();
-        D.cls = c; D.nnpe = S.nnpe; D.EP = S.EP; D.nxr = S.nxr; D.n_patches = S.n_patches; D.max_nodes = S.max_nodes; D.max_nx = S.max_nx;
+        D.cls = c; D.nnpe = S.nnpe; D.EP = S.EP; D.nxr = S.nxr; D.n_patches = S.n_patches; D.max_nodes = S.max_nodes; D.max_ncx = S.max_ncx; D.max_ncX = S.max_ncX;
         D.max_rows = S.max_rows; D.max_entries = S.max_entries; D.L = S.L;
         D.n_elems = S.n_elems; D.elem_offset = off;
         for (int64_t i = 0; i < S.n_elems; i++) e2i[S.elem_perm[i]] = off + i;
@@ -726,15 +668,15 @@ static int ensure_dynamic_smem(jfem_handle *h, const void *func, size_t bytes) {
 
 static bool ws_layout(const PatchSetDev &D, int x_all, WsSmem &L) {
     auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    const size_t xtile = sizeof(double) * 3 * (size_t)(x_all ? D.max_nodes : D.max_nx);
+    const size_t xtile = sizeof(double) * 2 * (size_t)D.max_ncx, Xtile = sizeof(double) * 2 * (size_t)(x_all ? D.max_ncx : D.max_ncX);
     L.strideA = (int)r128(D.L.bytesA()); L.strideB = (int)r128(D.L.bytesB()); L.strideC = (int)r128(D.L.bytesC());
     L.A = 128;
     L.B = L.A + 2 * L.strideA;
     L.C = L.B + 2 * L.strideB;
     L.stage = L.C + 2 * L.strideC;
     L.xs = (int)r128(L.stage + 2 * sizeof(double) * 3 * (size_t)D.max_entries);
-    L.Xs = (int)r128(L.xs + 2 * sizeof(double) * 3 * D.max_nodes);
-    L.total = (int)r128(L.Xs + 2 * xtile);
+    L.Xs = (int)r128(L.xs + 2 * xtile);
+    L.total = (int)r128(L.Xs + 2 * Xtile);
     return L.total <= 227 * 1024;
 }
 
@@ -743,13 +685,12 @@ template <int NNPE, int CLS, int MODE, class Pt, int T>
 static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const Pt &pt) {
     constexpr int NF = Pt::NF;
     auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    const size_t xtile = sizeof(double) * 3 * (size_t)(a.x_all ? D.max_nodes : D.max_nx);
+    const size_t Xtile = sizeof(double) * (size_t)a.Xs_cap;
     if constexpr (MODE == OP_LINEAR && T == WS_T && NF == 1 && (NNPE == 10 || NNPE == 8) && CLS == CLASS_AFFINE) {
         if (h->warp_specialised) {
             WsSmem L;
             if (ws_layout(D, a.x_all, L)) {
-                constexpr int GC = (CLS == CLASS_AFFINE && NNPE == 10) ? 1 : WS_GN;   // only the register-path gather (async_gather = 0) uses it
-                auto kws = patch_kernel_ws<NNPE, CLS, MODE, Pt, GC>;
+                auto kws = patch_kernel_ws<NNPE, CLS, MODE, Pt>;
                 JFEM_TRY(ensure_dynamic_smem(h, (const void *)kws, (size_t)L.total));
                 h->last_smem = L.total; h->last_blocks_per_sm = 1;
                 int grid = h->n_sms < D.n_patches ? h->n_sms : D.n_patches;
@@ -769,10 +710,10 @@ static int launch_set(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, const 
             }
         }
     }
-    const size_t tiles = sizeof(double) * (3 * (size_t)D.max_entries + (size_t)3 * D.max_nodes * (NF == 2 ? 2 : 1)) + xtile;
+    const size_t tiles = sizeof(double) * (3 * (size_t)D.max_entries + (size_t)a.xs_cap * (NF == 2 ? 2 : 1)) + Xtile;
     a.nbuf = 2;
-    size_t smem = r128(16 + 2 * (size_t)D.L.stride + tiles);
-    if (smem > 227 * 1024) { a.nbuf = 1; smem = r128(16 + (size_t)D.L.stride + tiles); }
+    size_t smem = r128(32 + 2 * (size_t)D.L.stride + tiles);
+    if (smem > 227 * 1024) { a.nbuf = 1; smem = r128(32 + (size_t)D.L.stride + tiles); }
     if (smem > 227 * 1024) { jfem_set_error("patch needs %zu bytes of shared memory; lower patch_elems", smem); return JFEM_EINVAL; }
     auto kern = patch_kernel<NNPE, CLS, MODE, Pt, T>;
     JFEM_TRY(ensure_dynamic_smem(h, (const void *)kern, smem));
@@ -890,13 +831,14 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         }
         a.blob = D.blob.p; a.n_patches = D.n_patches; a.stride = L.stride;
         a.offB = L.offB; a.offC = L.offC; a.bytesA = L.bytesA(); a.bytesB = L.bytesB(); a.bytesC = L.bytesC();
-        a.a_pn = L.off_pn - L.offA; a.a_xl = L.off_xl - L.offA; a.b_et = L.off_et - L.offB;
+        a.a_cx = L.off_cx - L.offA; a.a_cX = L.off_cX - L.offA; a.b_et = L.off_et - L.offB;
         a.c_qn = L.off_qn - L.offC; a.c_ql = L.off_ql - L.offC; a.c_jo = L.off_jo - L.offC;
-        a.max_nodes = D.max_nodes; a.max_nx = D.max_nx; a.max_entries = D.max_entries; a.x_all = D.nxr == 0 ? 1 : 0;
+        a.max_nodes = D.max_nodes; a.max_entries = D.max_entries; a.x_all = D.nxr == 0 ? 1 : 0;
+        a.xs_cap = 2 * D.max_ncx; a.Xs_cap = 2 * (a.x_all ? D.max_ncx : D.max_ncX); a.n_dofs = h->n_dofs();
         a.coords = h->coords.p; a.x = x; a.ulin = h->ulin.p; a.y = y; a.ipart = h->ipart.p; a.slot_node = h->slot_node.p;
         a.elem_offset = D.elem_offset;
         a.project = (flags & JFEM_PROJECT) ? 1 : 0; a.atomic_iface = atomic_iface;
-        a.fail = h->dflags.p; a.done = done; a.timing = h->timing.p; a.nbuf = 2; a.dbg = h->debug_skip; a.gmode = h->async_gather ? 1 : 0;
+        a.fail = h->dflags.p; a.done = done; a.timing = h->timing.p; a.nbuf = 2; a.dbg = h->debug_skip;
         int rc;
         switch (h->mesh.nnpe) {
             case 10: rc = dispatch_threads<10>(h, D, a, mode); break;

@@ -6,16 +6,16 @@
 
 namespace jf {
 
-// field accessors of an element thread: w[k] = (position of node k in the x tile) | (staging entry << 16)
+// field accessors of an element thread: w[k] = (offset of node k in the x tile, in doubles) | (staging entry << 16)
 struct PField {
     const double *base;
     const uint32_t *w;
-    JF_HD double operator()(int k, int c) const { return base[3 * (w[k] & 0xFFFFu) + c]; }
+    JF_HD double operator()(int k, int c) const { return base[(w[k] & 0xFFFFu) + c]; }
 };
-struct XField4 {   // coordinates of the 4 geometry nodes of an affine element (Tet10 vertices; Hex8 nodes 0, 1, 3, 4): slots packed two per word
+struct XField4 {   // coordinates of the 4 geometry nodes of an affine element (Tet10 vertices; Hex8 nodes 0, 1, 3, 4): offsets packed two per word
     const double *base;
     const uint32_t *xw;
-    JF_HD double operator()(int k, int c) const { return base[3 * ((k & 1) ? (xw[k >> 1] >> 16) : (xw[k >> 1] & 0xFFFFu)) + c]; }
+    JF_HD double operator()(int k, int c) const { return base[((k & 1) ? (xw[k >> 1] >> 16) : (xw[k >> 1] & 0xFFFFu)) + c]; }
 };
 
 // ---- phase 1 of one element (thread tid of a T-wide element group); et = element table of the patch

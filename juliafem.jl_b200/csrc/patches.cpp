@@ -317,8 +317,8 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
         static const int XN10[4] = {0, 1, 2, 3}, XN8[4] = {0, 1, 3, 4};
         const int *xn = nnpe == 8 ? XN8 : XN10;
         auto xidx = [&](int k) { for (int v = 0; v < nvx; v++) if (xn[v] == k) return v; return -1; };
-        // sizes needed for the layout: max_nx, max_rows
-        std::vector<int> nxs(S.n_patches, 0), nrw(S.n_patches, 0);
+        // sizes needed for the layout: chunk counts of the gather lists, max_rows
+        std::vector<int> ncxs(S.n_patches, 0), ncXs(S.n_patches, 0), nrw(S.n_patches, 0);
 #pragma omp parallel for schedule(dynamic, 64)
         for (int p = 0; p < S.n_patches; p++) {
             int64_t lo = (int64_t)p * EP, hi = std::min(lo + EP, S.n_elems);
@@ -332,15 +332,26 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                     if (xidx(k) >= 0) nx[j] = 1;
                 }
             nrw[p] = *std::max_element(cnt.begin(), cnt.end());
-            nxs[p] = (int)std::count(nx.begin(), nx.end(), (uint8_t)1);
+            // every node occupies the two chunks floor(3n/2), floor(3n/2)+1; ids ascending
+            int64_t last = -1, lastX = -1;
+            int nc = 0, ncX = 0;
+            for (size_t j = 0; j < ids.size(); j++) {
+                const int64_t c0 = (3 * (int64_t)ids[j]) >> 1;
+                nc += (c0 > last) + (c0 + 1 > last); last = c0 + 1;
+                if (nx[j]) { ncX += (c0 > lastX) + (c0 + 1 > lastX); lastX = c0 + 1; }
+            }
+            ncxs[p] = nc; ncXs[p] = ncX;
         }
-        for (int p = 0; p < S.n_patches; p++) { S.max_nx = std::max(S.max_nx, nxs[p]); S.max_rows = std::max(S.max_rows, nrw[p]); }
+        for (int p = 0; p < S.n_patches; p++) {
+            S.max_ncx = std::max(S.max_ncx, ncxs[p]); S.max_ncX = std::max(S.max_ncX, ncXs[p]); S.max_rows = std::max(S.max_rows, nrw[p]);
+        }
+        if (S.max_ncx > 32767) { jfem_set_error("patch needs too many gather chunks"); return JFEM_EINVAL; }
         if (S.max_rows > 255) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
         S.max_entries = EP * nnpe;
         auto r16 = [](int v) { return (v + 15) & ~15; };
         PatchLayout &L = S.L;
-        L.offA = 0; L.off_pn = 16; L.off_xl = L.off_pn + r16(4 * S.max_nodes);
-        L.offB = L.off_xl + r16(4 * S.max_nx); L.off_et = L.offB + 16;
+        L.offA = 0; L.off_cx = 16; L.off_cX = L.off_cx + r16(4 * S.max_ncx);
+        L.offB = L.off_cX + r16(4 * S.max_ncX); L.off_et = L.offB + 16;
         L.offC = L.off_et + r16(4 * (nnpe + S.nxr) * EP);
         L.off_qn = L.offC + 16; L.off_ql = L.off_qn + r16(4 * S.max_nodes);
         L.off_jo = L.off_ql + r16(S.max_nodes);
@@ -358,7 +369,9 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
             const int np = (int)ids.size(), nb = S.pnode_ptr[p];
             auto local_of = [&](int32_t n) { return (int)(std::lower_bound(ids.begin(), ids.end(), n) - ids.begin()); };
             std::vector<int32_t> cnt(np, 0);
-            std::vector<int32_t> xslot(np, -1);
+            std::vector<int32_t> xslot(np, -1);      // >= 0: the node's coordinates are needed; later its offset in the coordinate tile
+            std::vector<int32_t> xoff(np, 0);        // offset (in doubles) of the node in the x tile
+            std::vector<uint32_t> chx, chX;          // gather chunk lists
             std::vector<uint16_t> loc((size_t)ne * nnpe);
             for (int i = 0; i < ne; i++)
                 for (int k = 0; k < nnpe; k++) {
@@ -367,8 +380,22 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                     cnt[j]++;
                     if (xidx(k) >= 0) xslot[j] = 0;
                 }
-            int nx = 0;
-            for (int j = 0; j < np; j++) if (xslot[j] == 0) xslot[j] = nx++;
+            // gather chunks: node n = doubles 3n..3n+2 = chunks floor(3n/2), +1; its offset in the tile = 2 * (index of its
+            // first chunk) + (3n & 1)
+            for (int j = 0; j < np; j++) {
+                const int64_t d0 = 3 * (int64_t)ids[j], c0 = d0 >> 1;
+                if (chx.empty() || (int64_t)chx.back() < c0) chx.push_back((uint32_t)c0);
+                const int first = (int)chx.size() - 1 - ((int64_t)chx.back() > c0 ? 1 : 0);
+                if ((int64_t)chx.back() < c0 + 1) chx.push_back((uint32_t)(c0 + 1));
+                xoff[j] = 2 * first + (int)(d0 & 1);
+                if (xslot[j] == 0) {
+                    if (chX.empty() || (int64_t)chX.back() < c0) chX.push_back((uint32_t)c0);
+                    const int fX = (int)chX.size() - 1 - ((int64_t)chX.back() > c0 ? 1 : 0);
+                    if ((int64_t)chX.back() < c0 + 1) chX.push_back((uint32_t)(c0 + 1));
+                    xslot[j] = 2 * fX + (int)(d0 & 1);
+                }
+            }
+            const int ncx = (int)chx.size(), ncX = (int)chX.size();
             // reduce order q: descending contribution count, ascending id inside a count
             std::vector<int> order(np), qpos(np);
             std::iota(order.begin(), order.end(), 0);
@@ -394,7 +421,7 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
                         const int j = loc[(size_t)i * nnpe + k];
                         const int e = joff[fill[j]++] + qpos[j];
                         ent[(size_t)i * nnpe + k] = (uint16_t)e;
-                        lo_.idx[(size_t)i * lo_.ns + k] = (uint16_t)j;
+                        lo_.idx[(size_t)i * lo_.ns + k] = (uint16_t)xoff[j];
                         if (xidx(k) >= 0) lo_.idx[(size_t)i * lo_.ns + nnpe + xidx(k)] = (uint16_t)xslot[j];
                         lo_.idx[(size_t)i * lo_.ns + nnpe + nvx + k] = (uint16_t)e;
                     }
@@ -479,20 +506,18 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
             for (int t = 0; t < ne; t++) new_perm[lo + t] = S.elem_perm[lo + perm[t]];
             // ---- write the blob
             uint8_t *b = &S.blob[(size_t)p * L.stride];
-            const int32_t hdr[4] = {np, nx, ne, nrows | (S.ghosty[p] ? 0x10000 : 0)};   // bit 16: the patch reads ghost values
+            const int32_t hdr[4] = {np, ncx | (ncX << 16), ne, nrows | (S.ghosty[p] ? 0x10000 : 0)};   // bit 16: the patch reads ghost values
             memcpy(b + L.offA, hdr, 16); memcpy(b + L.offB, hdr, 16); memcpy(b + L.offC, hdr, 16);
-            uint32_t *bpn = reinterpret_cast<uint32_t *>(b + L.off_pn), *bxl = reinterpret_cast<uint32_t *>(b + L.off_xl);
+            uint32_t *bcx = reinterpret_cast<uint32_t *>(b + L.off_cx), *bcX = reinterpret_cast<uint32_t *>(b + L.off_cX);
             uint32_t *bet = reinterpret_cast<uint32_t *>(b + L.off_et);
             uint32_t *bqn = reinterpret_cast<uint32_t *>(b + L.off_qn);
             uint8_t *bql = b + L.off_ql;
             uint16_t *bjo = reinterpret_cast<uint16_t *>(b + L.off_jo);
-            for (int j = 0; j < np; j++) {
-                bpn[j] = (uint32_t)ids[j];
-                if (xslot[j] >= 0) bxl[xslot[j]] = (uint32_t)ids[j];
-            }
+            for (int j = 0; j < ncx; j++) bcx[j] = chx[j];
+            for (int j = 0; j < ncX; j++) bcX[j] = chX[j];
             for (int t = 0; t < ne; t++) {
                 const int i = perm[t];
-                for (int k = 0; k < nnpe; k++) bet[(size_t)k * EP + t] = (uint32_t)loc[(size_t)i * nnpe + k] | ((uint32_t)ent[(size_t)i * nnpe + k] << 16);
+                for (int k = 0; k < nnpe; k++) bet[(size_t)k * EP + t] = (uint32_t)xoff[loc[(size_t)i * nnpe + k]] | ((uint32_t)ent[(size_t)i * nnpe + k] << 16);
                 for (int v = 0; v < nvx; v += 2)
                     bet[(size_t)(nnpe + v / 2) * EP + t] =
                         (uint32_t)xslot[loc[(size_t)i * nnpe + xn[v]]] | ((uint32_t)xslot[loc[(size_t)i * nnpe + xn[v + 1]]] << 16);

@@ -9,7 +9,6 @@ h = _lib.Handle(10, m.coords, m.conn); h.set_material(0, (210e9, 0.3))
 h.set_option("debug_timing", 1)
 import os
 h.set_option("debug_skip", int(os.environ.get("JFEM_SKIP", "0")))
-h.set_option("async_gather", int(os.environ.get("JFEM_ASYNC", "0")))
 print("debug_skip =", os.environ.get("JFEM_SKIP", "0"))
 x = torch.from_numpy(mesh.test_vector(m.n_dofs)).cuda(); y = torch.empty_like(x)
 h.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -24,7 +23,7 @@ for k in range(3):
     base = c[0, 0]
     for it in range(7):
         r = c[it]
-        print(f"compute it {it} start {r[0]-base:6d} blobwait {max(r[5]-r[0],0):5d} ldg-issue {r[1]-max(r[5],r[0]):5d} stage_empty-wait {r[2]-r[1]:5d} ph1 {r[3]-r[2]:5d} store+sync {r[4]-r[3]:5d}")
+        print(f"compute it {it} start {r[0]-base:6d} wait x tile + part B {r[1]-r[0]:5d} wait stage_empty {r[2]-r[1]:5d} phase 1 {r[3]-r[2]:5d}")
     for it in range(7):
         r = hp[it]
-        print(f"helper  it {it} start {r[0]-base:6d} wait {r[1]-r[0]:5d} ph2 {r[2]-r[1]:5d} (lens {r[3]-r[1]:5d} rows {r[4]-r[3]:5d} [{r[6]} rows] stores {r[2]-r[4]:5d})")
+        print(f"helper  it {it} start {r[0]-base:6d} wait {r[1]-r[0]:5d} gather issue {r[5]-r[1]:5d} phase 2 {r[2]-r[5]:5d} (setup {r[3]-r[5]:5d} rows {r[4]-r[3]:5d} [{r[6]} rows] stores {r[2]-r[4]:5d})")

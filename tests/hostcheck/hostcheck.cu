@@ -24,29 +24,46 @@ static void run_set(const PatchSetHost &S, long long elem_offset, const MeshHost
                     std::vector<double> &ipart, long long n_owned, const double *land) {
     const PatchLayout &L = S.L;
     const bool x_all = S.nxr == 0;
-    std::vector<double> xs(3 * (size_t)S.max_nodes), Xs(3 * (size_t)(x_all ? S.max_nodes : S.max_nx)), stage(3 * (size_t)S.max_entries);
+    const long long nd = 3 * (long long)m.n_nodes, n_own3 = n_owned >= 0 ? 3 * n_owned : nd;
+    std::vector<double> xs(2 * (size_t)S.max_ncx), Xs(2 * (size_t)(x_all ? S.max_ncx : S.max_ncX)), stage(3 * (size_t)S.max_entries);
     for (int p = 0; p < S.n_patches; p++) {
         const uint8_t *b = &S.blob[(size_t)p * L.stride];
         const int32_t *hdr = reinterpret_cast<const int32_t *>(b);
-        const int np = hdr[0], nx = hdr[1], ne = hdr[2], nrows = hdr[3] & 0xFFFF;
-        const uint32_t *pn = reinterpret_cast<const uint32_t *>(b + L.off_pn), *xl = reinterpret_cast<const uint32_t *>(b + L.off_xl);
+        const int np = hdr[0], ncx = hdr[1] & 0xFFFF, ncX = hdr[1] >> 16, ne = hdr[2], nrows = hdr[3] & 0xFFFF;
+        const uint32_t *cx = reinterpret_cast<const uint32_t *>(b + L.off_cx), *cX = reinterpret_cast<const uint32_t *>(b + L.off_cX);
         const uint32_t *et = reinterpret_cast<const uint32_t *>(b + L.off_et);
         const uint32_t *qn = reinterpret_cast<const uint32_t *>(b + L.off_qn);
         const uint8_t *ql = b + L.off_ql;
         const uint16_t *jo = reinterpret_cast<const uint16_t *>(b + L.off_jo);
         bool seen_ghost = false;
-        for (int j = 0; j < np; j++)
-            for (int c = 0; c < 3; c++) {
-                // fused halo (matvec.cu node_ptr): ghost nodes (id >= n_owned) are read from the landing buffer, in ghost order
-                const bool ghost = n_owned >= 0 && (long long)pn[j] >= n_owned;
+        std::fill(xs.begin(), xs.end(), 1e300);
+        std::fill(Xs.begin(), Xs.end(), 1e300);
+        // gather_chunks of matvec.cu: chunk c = doubles 2c, 2c+1; doubles beyond the owned range come from the landing
+        // buffer (fused halo), doubles beyond the end of the vector are never copied
+        for (int j = 0; j < ncx; j++) {
+            if (j > 0 && cx[j] <= cx[j - 1]) { jfem_set_error("gather chunks of patch %d not ascending", p); throw 1; }
+            for (int e = 0; e < 2; e++) {
+                const long long d = 2LL * cx[j] + e;
+                if (d >= nd) continue;
+                const bool ghost = d >= n_own3;
                 seen_ghost |= ghost;
-                xs[3 * j + c] = ghost ? land[3 * ((size_t)pn[j] - (size_t)n_owned) + c] : x[3 * (size_t)pn[j] + c];
-                if (x_all) Xs[3 * j + c] = m.coords[3 * (size_t)pn[j] + c];
+                xs[2 * j + e] = ghost ? land[d - n_own3] : x[d];
+                if (x_all) Xs[2 * j + e] = m.coords[d];
             }
+        }
         if (!x_all)
-            for (int j = 0; j < nx; j++)
-                for (int c = 0; c < 3; c++) Xs[3 * j + c] = m.coords[3 * (size_t)xl[j] + c];
-        if (seen_ghost != ((hdr[3] & 0x10000) != 0)) { jfem_set_error("ghost flag of patch %d wrong", p); throw 1; }
+            for (int j = 0; j < ncX; j++)
+                for (int e = 0; e < 2; e++) {
+                    const long long d = 2LL * cX[j] + e;
+                    if (d < nd) Xs[2 * j + e] = m.coords[d];
+                }
+        // a chunk may drag in one double of a neighbouring (ghost) node that no element of the patch reads, so the flag may
+        // only be set when a ghost double is present, and must be set when one is read: checked through the poison below
+        if (((hdr[3] & 0x10000) != 0) && !seen_ghost) { jfem_set_error("ghost flag of patch %d set without ghost values", p); throw 1; }
+        if (!(hdr[3] & 0x10000) && n_owned >= 0)   // not flagged: the kernel may run it before the halo has landed
+            for (int j = 0; j < ncx; j++)
+                for (int e = 0; e < 2; e++)
+                    if (2LL * cx[j] + e >= n_own3 && 2LL * cx[j] + e < nd) xs[2 * j + e] = 1e300;
         std::fill(stage.begin(), stage.end(), 1e300);   // poison: every entry read must have been written
         for (int t = 0; t < ne; t++)
             element_phase<NNPE, CLS, OP_LINEAR, PtLinear, T>(pt, elem_offset + (long long)p * T + t, et, t, xs.data(), Xs.data(), nullptr, stage.data());
@@ -159,7 +176,7 @@ extern "C" double hostcheck_build_seconds(int nnpe, long long n_nodes, long long
     if (quality) {   // patches, nodes per patch (mean, max), interface nodes, partial slots, max coordinate nodes, blob stride
         const PatchSetHost &S = sets[CLASS_AFFINE].n_elems ? sets[CLASS_AFFINE] : sets[CLASS_GENERAL];
         quality[0] = S.n_patches; quality[1] = S.n_patches ? (double)S.pnode_ptr[S.n_patches] / S.n_patches : 0; quality[2] = S.max_nodes;
-        quality[3] = (double)hif.inodes.size(); quality[4] = (double)hif.n_partials; quality[5] = S.max_nx; quality[6] = S.L.stride;
+        quality[3] = (double)hif.inodes.size(); quality[4] = (double)hif.n_partials; quality[5] = S.max_ncX; quality[6] = S.L.stride;
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
