@@ -110,6 +110,7 @@ int jfem_destroy(jfem_handle *h) {
     h->nk_f.release(); h->red_partials.release(); h->cg_s.release(); h->nadj_ptr.release(); h->rowptr.release(); h->nadj.release();
     h->colind.release(); h->vals.release(); h->eblk.release(); h->dconn.release(); h->colour_elems.release(); h->e2i.release();
     h->send_nodes.release(); h->recv_nodes.release(); h->send_buf.release(); h->recv_buf.release();
+    h->timing.release(); h->xal.release(); h->cg_s.release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JFEM_OK;
@@ -128,7 +129,7 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
     } else if (!strcmp(key, "async_gather")) {
-        h->async_gather = value != 0;
+        // accepted for compatibility: the gather is always asynchronous (LDGSTS.128)
     } else if (!strcmp(key, "fused_halo")) {
         h->fused_halo = value != 0;
     } else if (!strcmp(key, "fused_interface")) {
@@ -142,8 +143,9 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
     } else if (!strcmp(key, "deterministic")) {
         h->deterministic = value != 0;
     } else if (!strcmp(key, "affine_fast_path")) {
+        // a request only: the closed forms exist for the linear-elastic operator alone, ensure_built() decides
         bool v = value != 0;
-        if (v != h->affine) { h->affine = v; h->built = false; }
+        if (v != h->affine) { h->affine = v; if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || h->mat_kind < 0) h->built = false; }
     } else {
         jfem_set_error("unknown option '%s'", key);
         return JFEM_EINVAL;
@@ -168,12 +170,12 @@ int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_para
     }
     if (per_element) { h->mat_per_elem.assign(params, params + (size_t)n_params * h->mesh.n_elems); h->mat_nparams = n_params; }
     else { h->mat_per_elem.clear(); h->mat_nparams = 0; h->matp.release(); }
-    const bool want_affine_prev = h->affine && h->mat_kind == JFEM_MAT_LINEAR_ELASTIC;
+    // the affine closed forms are only valid for the linear-elastic operator: the element classes (and with them the patch
+    // sets) depend on the material kind, see ensure_built()
+    const bool affine_prev = h->affine && (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || h->mat_kind < 0);
     h->mat_kind = kind;
     for (int i = 0; i < 4; i++) h->mat[i] = i < n_params ? params[i] : 0.0;
-    // the affine closed form is only valid for the linear-elastic operator
-    if (kind != JFEM_MAT_LINEAR_ELASTIC && h->affine) { h->affine = false; h->built = false; }
-    (void)want_affine_prev;
+    if ((h->affine && kind == JFEM_MAT_LINEAR_ELASTIC) != affine_prev) h->built = false;
     if (kind == JFEM_MAT_PERFECT_PLASTICITY && h->built && h->st_old.n == 0) h->built = false;
     if (h->built) return upload_material(h);
     return JFEM_OK;

@@ -206,7 +206,9 @@ extern "C" int jfem_comm_p2p_import(jfem_handle *h, const char *all_handles, con
         memcpy(&hf, all_handles + (size_t)s * 128 + 64, 64);
         void *pl = nullptr, *pf = nullptr;
         JFEM_CUDA(cudaIpcOpenMemHandle(&pl, hl, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_opened.push_back(pl);
         JFEM_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_opened.push_back(pf);
         h->p2p_peer_land[i] = (double *)pl;
         h->p2p_peer_flag[i] = (unsigned long long *)pf + h->rank;
         const int64_t off = recv_offsets[(size_t)s * h->n_ranks + h->rank];
@@ -226,6 +228,7 @@ extern "C" int jfem_comm_p2p_import(jfem_handle *h, const char *all_handles, con
         memcpy(&hf, all_handles + (size_t)s * 128 + 64, 64);
         void *pf = nullptr;
         JFEM_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        h->p2p_opened.push_back(pf);
         h->p2p_ctrl[s] = (unsigned long long *)pf;
     }
     h->p2p_ready = true;
@@ -351,6 +354,13 @@ extern "C" int jfem_comm_p2p_seq(jfem_handle *h, int64_t set_to, int64_t *seq) {
 }
 
 extern "C" int jfem_comm_destroy(jfem_handle *h) {
-    if (h && h->comm) { N.destroy(h->comm); h->comm = nullptr; h->n_ranks = 1; }
+    if (!h) return JFEM_OK;
+    // peer mappings opened by jfem_comm_p2p_import, then this rank's own landing / flag buffers
+    for (void *p : h->p2p_opened) cudaIpcCloseMemHandle(p);
+    h->p2p_opened.clear();
+    h->p2p_peer_land.clear(); h->p2p_peer_flag.clear(); h->p2p_ctrl.clear();
+    h->p2p_ready = false; h->halo_armed = false;
+    h->p2p_land.release(); h->p2p_flags.release(); h->p2p_ticket.release();
+    if (h->comm) { N.destroy(h->comm); h->comm = nullptr; h->n_ranks = 1; }
     return JFEM_OK;
 }

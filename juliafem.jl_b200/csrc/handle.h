@@ -22,7 +22,6 @@ struct jfem_handle {
     // options
     int patch_elems = 256;
     bool deterministic = true, affine = true, warp_specialised = true;
-    bool async_gather = true;           // option "async_gather": LDGSTS look-ahead gather in the ws kernel
     int debug_skip = 0;                 // profiling aid (option "debug_skip"): phases of the ws kernel to leave out
     int lane_window = 48;               // candidates examined per lane by the bank-aware lane assignment (0 = off)
     // material
@@ -56,6 +55,7 @@ struct jfem_handle {
     DevBuf<int> dflags;                 // [0] = fail flag (invalid deformation)
     // work vectors
     DevBuf<double> wx, wy;              // staging for host-pointer calls
+    DevBuf<double> xal;                 // 16-byte aligned copy of an operand that arrived misaligned (128-bit gathers)
     DevBuf<double> cg_r, cg_p, cg_Ap, cg_z, cg_dinv, nk_R, nk_du, nk_f;
     DevBuf<double> red_partials;
     DevBuf<CGScalars> cg_s;
@@ -87,6 +87,7 @@ struct jfem_handle {
     DevBuf<double> p2p_land;
     DevBuf<unsigned long long> p2p_flags;
     DevBuf<unsigned int> p2p_ticket;
+    std::vector<void *> p2p_opened;     // every pointer returned by cudaIpcOpenMemHandle (closed by jfem_comm_destroy)
     std::vector<double *> p2p_peer_land;
     std::vector<unsigned long long *> p2p_peer_flag, p2p_ctrl;
     unsigned long long p2p_ar_seq = 0;

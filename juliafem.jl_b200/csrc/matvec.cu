@@ -57,21 +57,24 @@ struct PatchKArgs {
     HaloFused hf;
 };
 
-// y[interface node] = sum of its partial slots (contiguous, ascending (set, patch) order); item = (node, component).
-// Nodes no element touches are listed with an empty slot range (y = 0).
+// y[interface node] = sum of its partial slots (contiguous, ascending (set, patch) order); one thread per node, three
+// components (one index lookup per node, 24 contiguous bytes per slot).  Nodes no element touches are listed with an empty
+// slot range (y = 0).
 __device__ __forceinline__ void iface_item(const uint32_t *__restrict__ inodes, const int32_t *__restrict__ ibase, const double *__restrict__ ipart,
-                                           double *__restrict__ y, long long i) {
-    const int node = (int)(i / 3), c = (int)(i - 3LL * node);
+                                           double *__restrict__ y, long long node) {
     const int b0 = ibase[node], b1 = ibase[node + 1];
-    const double *pp = ipart + 3LL * b0 + c;
-    double s = 0.0;
+    const double *pp = ipart + 3LL * b0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     int r = 0;
     for (; r + 2 <= b1 - b0; r += 2) {
-        const double v0 = __ldcg(pp + 3 * r), v1 = __ldcg(pp + 3 * r + 3);
-        s += v0; s += v1;
+        const double a0 = __ldcg(pp + 3 * r), a1 = __ldcg(pp + 3 * r + 1), a2 = __ldcg(pp + 3 * r + 2);
+        const double c0 = __ldcg(pp + 3 * r + 3), c1 = __ldcg(pp + 3 * r + 4), c2 = __ldcg(pp + 3 * r + 5);
+        s0 += a0; s1 += a1; s2 += a2;
+        s0 += c0; s1 += c1; s2 += c2;
     }
-    if (r < b1 - b0) s += __ldcg(pp + 3 * r);
-    y[3LL * inodes[node] + c] = s;
+    if (r < b1 - b0) { s0 += __ldcg(pp + 3 * r); s1 += __ldcg(pp + 3 * r + 1); s2 += __ldcg(pp + 3 * r + 2); }
+    double *d = y + 3LL * inodes[node];
+    d[0] = s0; d[1] = s1; d[2] = s2;
 }
 
 // Grid-wide barrier + interface reduction at the end of a (cooperatively launched) patch kernel.  Called by all threads.
@@ -84,7 +87,7 @@ __device__ __forceinline__ void iface_tail(const PatchKArgs &a) {
         __threadfence();
     }
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_inodes3; i += (long long)gridDim.x * blockDim.x)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_inodes3 / 3; i += (long long)gridDim.x * blockDim.x)
         iface_item(a.inodes, a.ibase, a.ipart, a.y, i);
 }
 
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(WS_T + WS_H, 1) patch_kernel_ws(PatchKArgs a, 
     if (a.tail) iface_tail(a);
 }
 
-// y[interface node] = sum of its partial slots (contiguous, ascending (set, patch) order).  One thread per (node, component).
+// y[interface node] = sum of its partial slots (contiguous, ascending (set, patch) order).  One thread per node.
 // Nodes no element touches are listed with an empty slot range (y = 0).
 __global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const int32_t *__restrict__ ibase, const double *__restrict__ ipart,
                                     double *__restrict__ y, long long n3, const int *done) {
@@ -543,7 +546,7 @@ __global__ void iface_reduce_kernel(const uint32_t *__restrict__ inodes, const i
     cudaGridDependencySynchronize();
     if (done && *done) return;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n3) iface_item(inodes, ibase, ipart, y, i);
+    if (3 * i < n3) iface_item(inodes, ibase, ipart, y, i);
 }
 
 __global__ void nodes_zero_kernel(const uint32_t *__restrict__ nodes, double *__restrict__ y, long long n3, const int *done) {
@@ -596,8 +599,11 @@ int ensure_built(jfem_handle *h) {
     if (h->built) return JFEM_OK;
     JFEM_CUDA(cudaSetDevice(h->device));
     auto t0 = std::chrono::steady_clock::now();
-    classify_elements(h->mesh, h->affine);
-    JFEM_TRY(build_patch_sets(h->mesh, h->patch_elems, h->affine, h->lane_window, h->n_ranks > 1 ? h->n_owned_nodes : -1, h->hsets, h->hif));
+    // closed-form (affine) element classes only for the linear-elastic operator: the general kernels index the coordinate
+    // tile by x-tile position, which the affine patch sets do not provide
+    const bool use_affine = h->affine && (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || h->mat_kind < 0);
+    classify_elements(h->mesh, use_affine);
+    JFEM_TRY(build_patch_sets(h->mesh, h->patch_elems, use_affine, h->lane_window, h->n_ranks > 1 ? h->n_owned_nodes : -1, h->hsets, h->hif));
     h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     int64_t off = 0;
     std::vector<int64_t> e2i(h->mesh.n_elems);
@@ -805,6 +811,12 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         jfem_set_error("tangent operator needs jfem_set_linearization"); return JFEM_ESTATE;
     }
     h->matvec_launches = 0;
+    const double *x_in = x;
+    if ((uintptr_t)x & 15) {   // the 128-bit gathers need a 16-byte aligned operand: take an aligned copy of a misaligned one
+        if (h->xal.n != (size_t)h->n_dofs()) JFEM_TRY(h->xal.alloc((size_t)h->n_dofs()));
+        JFEM_CUDA(cudaMemcpyAsync(h->xal.p, x, (size_t)h->n_dofs() * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        x = h->xal.p;
+    }
     const int atomic_iface = h->deterministic ? 0 : 1;
     const long long n3 = 3LL * (long long)h->inodes.n;
     if (atomic_iface && n3) {   // interface nodes are accumulated with atomicAdd
@@ -823,7 +835,7 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
         a.gbar = h->gbar.p; a.gbar_target = 0; a.inodes = h->inodes.p; a.ibase = h->ibase.p; a.n_inodes3 = n3;
         a.halo = 0; a.n_owned = 0xFFFFFFFFu;
         if (h->halo_armed) {
-            if (x != h->halo_x) { jfem_set_error("internal: fused halo armed for another vector"); return JFEM_ESTATE; }
+            if (x_in != h->halo_x) { jfem_set_error("internal: fused halo armed for another vector"); return JFEM_ESTATE; }
             a.halo = 1; a.n_owned = (uint32_t)h->n_owned_nodes;
             halo_fill_fused(h, a.hf);
             h->halo_armed = false;
@@ -849,7 +861,7 @@ int op_apply(jfem_handle *h, int mode, const double *x, double *y, int flags, co
     }
     if (!atomic_iface && n3 && !fused) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((n3 + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cfg.gridDim = dim3((unsigned)((n3 / 3 + 127) / 128)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
