@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py -- the driver-facing benchmark of the hot path (BASELINE.json: Tet10 elasticity matvec GDOF/s).
+"""bench.py -- the driver-facing benchmark of the hot path (BASELINE.json: Tet10 elasticity matvec GDOF/s at 1/2/4/8 B200;
+CG time-to-solve at 10 M DOF).
 
 A "step" is ONE matrix-free K.u over the whole mesh (BASELINE.json configs[1]: T1, Tet10 cantilever 88x22x22 cells,
 1 075 275 DOF; for N GPUs the box grows to 88x22x(22N) cells and is slab-partitioned by contiguous node ranges, i.e.
@@ -12,9 +13,17 @@ capture fails).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload T1|T10|H100|...]
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = same metric through the C ABI with
-pinned HOST buffers (H2D + D2H inside the timed region), `roofline` = algorithmic bytes (35 B/DOF Tet10, 35.7 Hex8,
-SURVEY.md 8d) / measured step time vs the measured HBM peak, `cpu_baseline` = the CPU oracle timed on the host cores.
+Prints ONE JSON line (rank 0).  Besides the contract keys:
+  parity            BEFORE timing, the GPU K.u of the very mesh that is timed is compared with the CPU oracle's matrix-free
+                    K.u (whole mesh when it is small enough, otherwise all rows of a node sample that always contains the
+                    partition-interface layer); every rank checks its own rows; the run FAILS above 1e-12 (north_star).
+  e2e               same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
+  roofline          algorithmic bytes (35 B/DOF Tet10, 35.7 Hex8) / measured step time vs the measured HBM peak
+  cpu_baseline      the reference's CPU K.v (assembled CSR SpMV, oracle port) on the SAME mesh when it fits, all host threads
+  cg_time_to_solve  plain CG to ||r|| <= 1e-8 ||b|| on the 10.9 M-DOF Tet10 cantilever (N = 1) / on the workload itself (N > 1)
+  assembly          coloured CSR assembly throughput (elements/s, fraction of the 3.7 KB/element HBM roofline)
+  hex8_weak         BASELINE.json configs[2]: Hex8 lattice, 12.5 M DOF per GPU (99.6 M DOF at N = 8), matrix-free K.u, with its
+                    own parity check -- the per-N values give the weak-scaling efficiency of the 100 M-DOF target
 """
 from __future__ import annotations
 
@@ -37,29 +46,49 @@ WORKLOADS = {   # name: (elem_type, cells/nodes, box lengths)
     "TS": (10, (24, 6, 6), (4.0, 1.0, 1.0)),          # small smoke size
     "H100": (8, (321, 321, 321), None),               # 99 228 483 DOF (configs[2]); nodes per direction
     "H12": (8, (161, 161, 161), None),                # 12.5 M DOF
+    "HS": (8, (25, 25, 25), None),                    # small smoke size
 }
 BYTES_PER_DOF = {10: 35.0, 8: 35.0 + 2.0 / 3.0, 4: 35.0}
+ASSEMBLY_BYTES_PER_ELEM = 3.7e3       # values written (2.8 KB) + state + connectivity/coordinates, Tet10
+FP64_FLOP_PER_ELEM = {10: 343 * 2 + 170.0, 8: 1400.0}   # SASS of the closed forms: DFMA counted twice (Tet10 affine: 343 DFMA + 170 DADD/DMUL)
 METRIC = "tet10_elasticity_matvec_gdofs"
+PARITY_TOL = 1e-12
+MAT = (210e9, 0.3)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def lattice_args(name, n_gpus=1):
+    """(elem_type, dims, box) of the workload weak-scaled to n_gpus (the box grows in z)."""
+    et, dims, box = WORKLOADS[name]
+    if et == 10:
+        cx, cy, cz = dims
+        return et, (cx, cy, cz * n_gpus), (box[0], box[1], box[2] * n_gpus)
+    nx, ny, nz = dims
+    return et, (nx, ny, (nz - 1) * n_gpus + 1), 1.0 / (nx - 1)
 
 
 def build_mesh(name, n_gpus=1):
     from juliafem.jl_b200 import mesh
-    et, dims, box = WORKLOADS[name]
+    et, dims, box = lattice_args(name, n_gpus)
     if et == 10:
-        cx, cy, cz = dims
-        return mesh.tet10_kuhn(cx, cy, cz * n_gpus, box[0], box[1], box[2] * n_gpus)
-    nx, ny, nz = dims
-    return mesh.hex8_lattice(nx, ny, (nz - 1) * n_gpus + 1, 1.0 / (nx - 1))
+        return mesh.tet10_kuhn(dims[0], dims[1], dims[2], box[0], box[1], box[2])
+    return mesh.hex8_lattice(dims[0], dims[1], dims[2], box)
 
 
 def workload_label(name, n_gpus=1):
     """'T1: Tet10 matrix-free K.u, <n> DOF, <m> elements' without building the mesh (same text as the GPU arm's config)."""
-    et, dims, _ = WORKLOADS[name]
+    et, dims, _ = lattice_args(name, n_gpus)
     if et == 10:
-        cx, cy, cz = dims[0], dims[1], dims[2] * n_gpus
+        cx, cy, cz = dims
         nd, ne = 3 * (2 * cx + 1) * (2 * cy + 1) * (2 * cz + 1), 6 * cx * cy * cz
     else:
-        nx, ny, nz = dims[0], dims[1], (dims[2] - 1) * n_gpus + 1
+        nx, ny, nz = dims
         nd, ne = 3 * nx * ny * nz, (nx - 1) * (ny - 1) * (nz - 1)
     return f"{name}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {nd} DOF, {ne} elements"
 
@@ -75,7 +104,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the spin-up + timed region."""
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
@@ -84,7 +113,7 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -92,70 +121,116 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([s.strip() for s in line.split(",")])
+            self.rows.append((time.perf_counter(), [s.strip() for s in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_from=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t_from is None or t >= t_from] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
 
-def cpu_baseline(workload, seconds=12.0):
+# ------------------------------------------------------------------------------------------------ CPU side (oracle)
+
+def cpu_baseline(workload, seconds=12.0, threads=None):
     """The reference's CPU K.v is a sparse matrix-vector product on the assembled K
-    (src/element_assembly_structures.jl:307-309).  Timed with the oracle port on a bounded sample: a sub-box of the
-    workload (same element type, spacing, material) small enough that assembly + timing stay within ~10-30 s."""
+    (src/element_assembly_structures.jl:307-309).  Timed with the oracle port on all host threads: on the workload's own
+    mesh when its CSR fits the time budget (<= 1.6 M DOF: T1 is ~92 M non-zeros), otherwise on a sub-box of it."""
     from oracle import oracle as O
     from juliafem.jl_b200 import mesh
+    nthr = O.set_num_threads(threads or host_threads())
     et, dims, box = WORKLOADS[workload]
-    if et == 10:
+    nd = int(workload_label(workload).split(", ")[1].split()[0])
+    same = nd <= 1_600_000
+    if same:
+        m = build_mesh(workload)
+        sample = f"the workload's own mesh ({m.n_dofs} DOF): assembled CSR SpMV, OpenMP"
+    elif et == 10:
         m = mesh.tet10_kuhn(32, 12, 12, 4.0 * 32 / 88, 12 / 22, 12 / 22)
         sample = "Tet10 32x12x12-cell sub-box of the workload (121 875 DOF): assembled CSR SpMV, OpenMP"
     else:
         m = mesh.hex8_lattice(49, 49, 49, 1.0 / 320)
         sample = "Hex8 49^3-node sub-box (352 947 DOF): assembled CSR SpMV, OpenMP"
+    if os.environ.get("JFEM_BENCH_CPU_SMALL"):           # (the CLI test keeps the reference arm short)
+        m, same = mesh.tet10_kuhn(12, 4, 4, 1.5, 0.5, 0.5), False
+        sample = "Tet10 12x4x4-cell sub-box (test mode): assembled CSR SpMV, OpenMP"
     t0 = time.perf_counter()
-    rp, ci, vals, _ = O.assemble_csr(et, m.coords, m.conn, par=(210e9, 0.3))
+    rp, ci, vals, _ = O.assemble_csr(m.elem_type, m.coords, m.conn, par=MAT)
     t_asm = time.perf_counter() - t0
     u = mesh.test_vector(m.n_dofs)
     O.spmv(rp, ci, vals, u)
-    seconds = float(os.environ.get("JFEM_BENCH_CPU_SECONDS", seconds))     # (the CLI test shortens the timing loop)
+    seconds = float(os.environ.get("JFEM_BENCH_CPU_SECONDS", seconds))
     best, t_end, reps = 1e30, time.perf_counter() + min(seconds, 8.0), 0
     while time.perf_counter() < t_end or reps < 3:
         t0 = time.perf_counter()
         O.spmv(rp, ci, vals, u)
         best = min(best, time.perf_counter() - t0)
         reps += 1
-    t0 = time.perf_counter()
-    O.matfree(et, m.coords, m.conn, u)
-    t_mf = time.perf_counter() - t0
-    return {"value": m.n_dofs / best / 1e9, "unit": "GDOF/s", "cores": O.num_threads(), "kind": "port", "ms_per_step": best * 1e3,
-            "sample": sample + f"; best of {reps}; assembly of the sample took {t_asm:.2f} s ({m.n_elems / t_asm:.0f} elements/s); "
-                               f"matrix-free oracle K.u {m.n_dofs / t_mf / 1e9:.4f} GDOF/s"}
+    return {"value": m.n_dofs / best / 1e9, "unit": "GDOF/s", "cores": nthr, "kind": "port", "ms_per_step": best * 1e3, "same_mesh": bool(same),
+            "sample": sample + f"; best of {reps}; {nthr} OpenMP threads; assembly of that mesh took {t_asm:.2f} s "
+                               f"({m.n_elems / t_asm:.0f} elements/s)"}
 
 
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia (not installed, and
     the package does not load as shipped), so this arm times the oracle port of its CPU K.v with all host
-    threads, rank 0 only."""
+    threads, rank 0 only (under torchrun the other ranks exit; OMP_NUM_THREADS=1 set by torchrun is overridden)."""
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     cb = cpu_baseline(args.workload, seconds=10.0)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_label(args.workload) + " -- CPU arm: assembled CSR K.v of the reference on a bounded sample of this mesh "
-                                  "(see cpu_baseline.sample)"},
+           "config": {"workload": workload_label(args.workload) + " -- CPU arm: assembled CSR K.v of the reference (oracle port), "
+                                  + ("on this very mesh" if cb["same_mesh"] else "on a bounded sample of this mesh (see cpu_baseline.sample)"),
+                      "same_mesh": cb["same_mesh"], "omp_threads": cb["cores"]},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
+
+def parity_check(pp, y_local, u_local, world, full_limit=1_600_000, sample_nodes=12000, seed=7):
+    """GPU K.u (projected) of this rank's mesh against the oracle's matrix-free K.u on the same local mesh (owned +
+    ghost elements: the owned rows are complete).  Small meshes: every owned row.  Large meshes: all rows of a node
+    sample = every owned node of an element that touches a ghost node (the halo path) capped at half the sample, plus
+    random owned nodes; only the elements touching the sample are integrated.  Returns (max rel err, #dofs, seconds)."""
+    from oracle import oracle as O
+    O.set_num_threads(max(1, host_threads() // world))
+    t0 = time.perf_counter()
+    n_owned = pp.n_owned
+    conn = pp.conn_local
+    et = pp.elem_type
+    if 3 * n_owned <= full_limit:
+        nodes = np.arange(1, n_owned + 1)
+        sub = conn
+    else:
+        rng = np.random.default_rng(seed + pp.rank)
+        ghosty = (conn > n_owned).any(axis=1)
+        near = np.unique(conn[ghosty])
+        near = near[near <= n_owned]
+        if near.size > sample_nodes // 2:
+            near = rng.choice(near, sample_nodes // 2, replace=False)
+        rest = rng.choice(n_owned, min(n_owned, sample_nodes - near.size), replace=False) + 1
+        nodes = np.unique(np.concatenate([near, rest]))
+        mark = np.zeros(pp.local_nodes.size + 1, dtype=bool)
+        mark[nodes] = True
+        sub = conn[mark[conn].any(axis=1)]
+    ref = O.matfree(et, pp.coords_local, sub, u_local, par=MAT, fixed_dofs=pp.fixed_local if pp.fixed_local.size else None)
+    rows = (3 * (nodes[:, None] - 1) + np.arange(3)[None, :]).ravel()
+    scale = np.abs(ref[: 3 * n_owned]).max()
+    err = float(np.abs(y_local[rows] - ref[rows]).max() / (scale if scale > 0 else 1.0))
+    return err, int(rows.size), time.perf_counter() - t0
+
+
+# ------------------------------------------------------------------------------------------------ GPU side
 
 def main():
     ap = argparse.ArgumentParser()
@@ -167,12 +242,15 @@ def main():
     ap.add_argument("--patch", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (jfem_set_option), repeatable")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU legs (cpu_baseline AND the oracle parity check)")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--spinup", type=float, default=0.8, help="seconds of untimed load before the warm-up steps (clock ramp)")
     ap.add_argument("--graph", type=int, default=-1, help="1: replay the timed loop as one CUDA graph (no host launch jitter between "
                     "ranks); 0: launch every step from the host; default: 1")
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
-    ap.add_argument("--cg", action="store_true", help="also time a full CG solve (||r|| <= 1e-8 ||b||) on the workload")
+    ap.add_argument("--cg", default="auto", help="CG time-to-solve: workload name, 'same', 'none' or 'auto' (T10 at N=1, 'same' at N>1)")
+    ap.add_argument("--hex8", default="auto", help="secondary Hex8 weak-scaling measurement: workload name per GPU, 'none' or 'auto' (H12)")
+    ap.add_argument("--no-extras", action="store_true", help="skip cg / assembly / hex8_weak (kernel timing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -181,6 +259,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // world))   # torchrun sets 1: the patch builder and the oracle use OpenMP
 
     import torch
     import torch.distributed as dist
@@ -193,26 +272,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank)       # every rank watches its own GPU, from before the spin-up on
+    sampler.start()
 
     from juliafem.jl_b200.distributed import PartitionedProblem, torch_all_gather_object, torch_broadcast_bytes
-    m = build_mesh(args.workload, world)
-    et = m.elem_type
-    fixed_g = mesh.clamp_dofs(m)
-    total_dofs = m.n_dofs
-    pp = PartitionedProblem(m, rank, world, local_rank, material=(_lib.MAT_LINEAR_ELASTIC, (210e9, 0.3)), fixed_dofs=fixed_g,
-                            options=dict([("patch_elems", args.patch)] if args.patch else [], **{k: float(v) for k, v in (o.split("=") for o in args.opt)}) or None)
-    h = pp.handle
-    n_local_dofs, n_own_dofs = 3 * pp.local_nodes.size, 3 * pp.n_owned
-    h.set_stream(torch.cuda.current_stream().cuda_stream)
-    if world > 1:
-        pp.init_comm(torch_broadcast_bytes(dist, dev))
-        if not args.nccl_halo:
-            pp.init_p2p(torch_all_gather_object(dist))
-
-    u_full = mesh.test_vector(total_dofs, fixed_g)
-    u_host = pp.scatter_vector(u_full)
-    x = torch.from_numpy(u_host).to(dev)
-    y = torch.empty_like(x)
+    lib_opts = dict([("patch_elems", args.patch)] if args.patch else [], **{k: float(v) for k, v in (o.split("=") for o in args.opt)}) or None
+    do_cpu = not args.no_cpu
     flush = None if args.no_flush else torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def barrier():
@@ -220,85 +285,134 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        h.matvec(x, y, flags=_lib.PROJECT)
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # untimed spin-up: a GPU that has been idle (setup is host work) needs tens of ms under load to reach its boost clock;
-    # with W warm-up steps of ~50 us each a rank could still be ramping during the timed region and stall its neighbours
-    # (the number of spin-up steps must be the same on every rank: each step is a halo exchange with the neighbours)
-    step()                                   # first call builds the patches (host work): keep it out of the step-time estimate
-    torch.cuda.synchronize()
-    t_spin = time.perf_counter()
-    for _ in range(10):
-        step()
-    torch.cuda.synchronize()
-    t_step = torch.tensor([(time.perf_counter() - t_spin) / 10], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_step, op=dist.ReduceOp.MAX)
-    n_spin = int(min(20000, max(0, args.spinup / max(float(t_step.item()), 1e-6))))
-    for _ in range(n_spin):
-        step()
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    info = h.info()
-    launches_before = int(info.total_launches)
+    def setup_problem(workload):
+        et, dims, box = lattice_args(workload, world)
+        pp = PartitionedProblem.from_lattice(et, dims, box, rank, world, local_rank, material=(_lib.MAT_LINEAR_ELASTIC, MAT), options=lib_opts)
+        pp.handle.set_stream(torch.cuda.current_stream().cuda_stream)
+        if world > 1:
+            pp.init_comm(torch_broadcast_bytes(dist, dev))
+            if not args.nccl_halo:
+                pp.init_p2p(torch_all_gather_object(dist))
+        gd = pp.local_global_dofs()
+        u_host = mesh.hashed_vector(gd)
+        if pp.fixed_local.size:
+            u_host[pp.fixed_local - 1] = 0.0
+        return pp, u_host
 
-    sampler = ClockSampler(local_rank)       # every rank watches its own GPU
-    sampler.start()
-    use_graph = True if args.graph < 0 else bool(args.graph)
-
-    def timed_loop(ev):
-        for k in range(args.steps):
-            if flush is not None:
-                flush.fill_(float(k))
-            ev[k][0].record()
-            step()
-            ev[k][1].record()
-
-    host_s = None
-    if use_graph:
-        # The K timed steps (L2 flush, event, K.u, event) are captured once and replayed as ONE graph launch: every rank's
-        # GPU then runs its K steps back to back with no host in the loop, so a late host launch on one rank cannot stall
-        # its neighbours at the halo gate.  Same kernels, same events, same barrier + synchronize bracket.
-        ok = 1.0
-        try:
-            ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(args.steps)]
-            g = torch.cuda.CUDAGraph()
-            cap = torch.cuda.Stream()
-            torch.cuda.synchronize()
-            h.set_stream(cap.cuda_stream)          # (synchronises the old stream: must happen outside the capture)
-            with torch.cuda.graph(g, stream=cap):
-                timed_loop(ev)
-        except Exception as exc:                   # capture unsupported here: fall back to per-step host launches
-            ok = 0.0
-            print(f"[bench] CUDA graph capture failed ({str(exc)[:120]}); timing with per-step launches", file=sys.stderr, flush=True)
+    def check_parity(pp, u_host, x, y):
+        """K.u of this mesh against the oracle, all ranks; returns the dict for the JSON line (rank 0 aggregates)."""
+        pp.handle.matvec(x, y, flags=_lib.PROJECT)
         torch.cuda.synchronize()
-        h.set_stream(torch.cuda.current_stream().cuda_stream)
-        if world > 1:                              # every rank must take the same path
-            t = torch.tensor([ok], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            ok = float(t.item())
-        if ok:
-            barrier()
-            g.replay()
-            barrier()
-        else:
-            use_graph = False
-            if world > 1:                          # ranks may have enqueued different numbers of exchanges: re-synchronise the halo sequence
-                t = torch.tensor([float(h.comm_p2p_seq())], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                h.comm_p2p_seq(int(t.item()) + 2)
-    if not use_graph:
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        err, ndofs, secs = parity_check(pp, y.cpu().numpy(), u_host, world)
+        worst = allmax(err)
+        secs = allmax(secs)
+        tot = ndofs
+        if world > 1:
+            t = torch.tensor([float(ndofs)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            tot = int(t.item())
+        return {"rel_err": worst, "tol": PARITY_TOL, "ok": bool(worst <= PARITY_TOL), "checked_dofs": tot, "ranks_checked": world,
+                "oracle": "matrix-free K.u of the CPU oracle (oracle/jfem_oracle.c) on every rank's local mesh, same vector, Dirichlet rows zeroed",
+                "oracle_seconds": secs}
+
+    def time_matvec(pp, x, y, steps, warmup, spinup):
+        """W warm-up + K timed K.u (L2 flushed in between), as one CUDA graph when possible.  Returns per-step ms array, info."""
+        h = pp.handle
+
+        def step():
+            h.matvec(x, y, flags=_lib.PROJECT)
+
+        step()
+        torch.cuda.synchronize()
+        t_spin = time.perf_counter()
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        t_step = allmax((time.perf_counter() - t_spin) / 10)
+        n_spin = int(min(20000, max(0, spinup / max(t_step, 1e-6))))     # same count on every rank: each step is a halo exchange
+        for _ in range(n_spin):
+            step()
+        torch.cuda.synchronize()
+        for _ in range(warmup):
+            step()
         barrier()
-        t0 = time.perf_counter()
-        timed_loop(ev)
-        host_s = (time.perf_counter() - t0) / args.steps
-        barrier()
-    launches_timed = int(h.info().total_launches) - launches_before     # kernels of the library launched inside the timed region
-    times = np.array([a.elapsed_time(b) for a, b in ev])       # ms, device time of each step
+        launches_before = int(h.info().total_launches)
+        t_timed = time.perf_counter()
+        use_graph = True if args.graph < 0 else bool(args.graph)
+
+        def timed_loop(ev):
+            for k in range(steps):
+                if flush is not None:
+                    flush.fill_(float(k))
+                ev[k][0].record()
+                step()
+                ev[k][1].record()
+
+        host_s = None
+        if use_graph:
+            ok = 1.0
+            try:
+                ev = [(torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True)) for _ in range(steps)]
+                g = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream()
+                torch.cuda.synchronize()
+                h.set_stream(cap.cuda_stream)          # (synchronises the old stream: must happen outside the capture)
+                with torch.cuda.graph(g, stream=cap):
+                    timed_loop(ev)
+            except Exception as exc:                   # capture unsupported here: fall back to per-step host launches
+                ok = 0.0
+                print(f"[bench] CUDA graph capture failed ({str(exc)[:120]}); timing with per-step launches", file=sys.stderr, flush=True)
+            torch.cuda.synchronize()
+            h.set_stream(torch.cuda.current_stream().cuda_stream)
+            if world > 1:                              # every rank must take the same path
+                t = torch.tensor([ok], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ok = float(t.item())
+            if ok:
+                barrier()
+                g.replay()
+                barrier()
+            else:
+                use_graph = False
+                if world > 1:                          # ranks may have enqueued different numbers of exchanges: re-synchronise the halo sequence
+                    t = torch.tensor([float(h.comm_p2p_seq())], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    h.comm_p2p_seq(int(t.item()) + 2)
+        if not use_graph:
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            barrier()
+            t0 = time.perf_counter()
+            timed_loop(ev)
+            host_s = (time.perf_counter() - t0) / steps
+            barrier()
+        launches = int(h.info().total_launches) - launches_before
+        times = np.array([a.elapsed_time(b) for a, b in ev])
+        return times, {"use_graph": use_graph, "host_s": host_s, "launches": launches, "t_timed": t_timed}
+
+    # ================================================================ main workload
+    pp, u_host = setup_problem(args.workload)
+    h = pp.handle
+    et = pp.elem_type
+    total_dofs, total_elems = 3 * pp.n_nodes_global, pp.n_elems_global
+    n_local_dofs, n_own_dofs = 3 * pp.local_nodes.size, 3 * pp.n_owned
+    x = torch.from_numpy(u_host).to(dev)
+    y = torch.empty_like(x)
+    parity = None
+    if do_cpu and not args.no_parity:
+        parity = check_parity(pp, u_host, x, y)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity check failed", "parity": parity}), flush=True)
+            raise SystemExit(3)
+    times, tinfo = time_matvec(pp, x, y, args.steps, args.warmup, args.spinup)
+    info = h.info()
     ms = float(times.mean())
     per_rank = None
     if world > 1:
@@ -306,10 +420,8 @@ def main():
         allst = [torch.zeros_like(st) for _ in range(world)]
         dist.all_gather(allst, st)
         per_rank = [[round(float(v), 5) for v in a.cpu()] for a in allst]      # mean, min, median, max of every rank (ms)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    clocks = sampler.stop()
+        ms = allmax(ms)
+    clocks = sampler.stop(tinfo["t_timed"])
     if world > 1:
         mine = torch.tensor([clocks["sm_mhz"] or 0.0, float(len(clocks["reasons"]))], device=dev, dtype=torch.float64)
         allc = [torch.zeros_like(mine) for _ in range(world)]
@@ -334,32 +446,87 @@ def main():
     for _ in range(n_e2e):
         h.matvec(xn, yn, flags=_lib.PROJECT)
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = allmax((time.perf_counter() - t0) / n_e2e)
     checksum = float(np.abs(yn[:n_own_dofs]).sum())
+    if world > 1:
+        t = torch.tensor([checksum], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        checksum = float(t.item())
 
-    cg_out = None
-    if args.cg:
-        # CG time-to-solve (second half of BASELINE.json's metric): uniform body load in -z, clamp x = 0,
-        # plain (unpreconditioned) CG exactly as the reference's cg_solve_matfree_gpu!, relative stop 1e-8.
-        bfull = np.zeros(total_dofs); bfull[2::3] = -1.0e3
-        bd = torch.from_numpy(pp.scatter_vector(bfull)).to(dev)
+    def cg_solve(pp_, label):
+        """plain (unpreconditioned) CG exactly as the reference's cg_solve_matfree_gpu!, relative stop 1e-8; uniform body
+        load in -z lumped to the nodes, clamp x = 0"""
+        hh = pp_.handle
+        b = np.zeros(3 * pp_.local_nodes.size)
+        b[2::3] = -1.0e3
+        bd = torch.from_numpy(b).to(dev)
         xd = torch.zeros_like(bd)
+        hh.matvec(xd, torch.empty_like(xd), flags=_lib.PROJECT)    # (patch build outside the timing)
         barrier()
         t0 = time.perf_counter()
-        _, cg_it, cg_res = h.cg(bd, x0=xd, tol=1e-8, relative=True, max_iter=200000)
+        _, cg_it, cg_res = hh.cg(bd, x0=xd, tol=1e-8, relative=True, max_iter=200000)
         torch.cuda.synchronize()
-        cg_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([cg_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            cg_s = float(t.item())
-        cg_out = {"workload": args.workload, "dofs": total_dofs, "iterations": int(cg_it), "seconds": cg_s, "final_abs_residual": float(cg_res),
-                  "tol": "||r|| <= 1e-8 ||b|| (relative; the reference's default is absolute 1e-6)", "ms_per_iteration": 1e3 * cg_s / max(cg_it, 1),
-                  "preconditioner": "none (as the reference)"}
+        cg_s = allmax(time.perf_counter() - t0)
+        return {"workload": label, "dofs": 3 * pp_.n_nodes_global, "iterations": int(cg_it), "seconds": cg_s, "final_abs_residual": float(cg_res),
+                "converged": bool(cg_it < 200000), "tol": "||r|| <= 1e-8 ||b|| (relative; the reference's default is absolute 1e-6)",
+                "ms_per_iteration": 1e3 * cg_s / max(cg_it, 1), "preconditioner": "none (as the reference)",
+                "setup_s": float(hh.info().setup_seconds), "gdof_iterations_per_s": 3 * pp_.n_nodes_global * cg_it / cg_s / 1e9}
+
+    cg_out = asm_out = hex_out = None
+    if not args.no_extras:
+        cg_wl = args.cg
+        if cg_wl == "auto":
+            cg_wl = "T10" if world == 1 else "same"
+        if cg_wl == "same" or cg_wl == args.workload:
+            cg_out = cg_solve(pp, workload_label(args.workload, world))
+        elif cg_wl != "none":
+            pp2, _ = setup_problem(cg_wl)
+            cg_out = cg_solve(pp2, workload_label(cg_wl, world))
+            pp2.handle.close()
+        if world == 1:
+            # coloured CSR assembly (linear elastic Tet10, 98 304 elements): pattern build + one assembly pass
+            ma = mesh.tet10_kuhn(64, 16, 16, 4.0, 1.0, 1.0)
+            ha = _lib.Handle(10, ma.coords, ma.conn, device=local_rank)
+            ha.set_material(_lib.MAT_LINEAR_ELASTIC, MAT)
+            ha.set_stream(torch.cuda.current_stream().cuda_stream)
+            t0 = time.perf_counter()
+            ha.csr_pattern()
+            t_pat = time.perf_counter() - t0
+            ua = torch.zeros(ma.n_dofs, dtype=torch.float64, device=dev)
+            ha.assemble_csr(ua)
+            torch.cuda.synchronize()
+            ts = []
+            for k in range(5):
+                if flush is not None:
+                    flush.fill_(float(k))
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); ha.assemble_csr(ua); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t_asm = float(np.mean(ts)) * 1e-3
+            peak, _ = peaks()
+            asm_out = {"workload": f"Tet10 64x16x16 cells, {ma.n_elems} elements, {ma.n_dofs} DOF, linear elastic, coloured scatter into the reference's CSR pattern",
+                       "elements_per_s": ma.n_elems / t_asm, "ms": t_asm * 1e3, "pattern_build_s": t_pat,
+                       "bytes_per_element": ASSEMBLY_BYTES_PER_ELEM, "frac_hbm_roofline": ASSEMBLY_BYTES_PER_ELEM * ma.n_elems / t_asm / 1e9 / peak,
+                       "l2": "flushed between repetitions" if flush is not None else "not flushed"}
+            ha.close()
+        hx = args.hex8
+        if hx == "auto":
+            hx = "H12" if WORKLOADS[args.workload][0] == 10 else "none"
+        if hx != "none":
+            pp3, u3 = setup_problem(hx)
+            x3 = torch.from_numpy(u3).to(dev)
+            y3 = torch.empty_like(x3)
+            par3 = check_parity(pp3, u3, x3, y3) if (do_cpu and not args.no_parity) else None
+            t3, _ = time_matvec(pp3, x3, y3, max(5, args.steps // 2), 3, 0.2)
+            ms3 = allmax(float(t3.mean()))
+            nd3 = 3 * pp3.n_nodes_global
+            peak, _ = peaks()
+            hex_out = {"workload": workload_label(hx, world) + " (BASELINE.json configs[2]: 12.5 M DOF per GPU, weak scaling; 99.6 M DOF at 8 GPUs)",
+                       "value": nd3 / (ms3 * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms3, "n_gpus": world, "dofs": nd3,
+                       "roofline_frac": BYTES_PER_DOF[8] * nd3 / world / (ms3 * 1e-3) / 1e9 / peak, "parity": par3,
+                       "setup_s": float(pp3.handle.info().setup_seconds), "n_patches": int(pp3.handle.info().n_patches)}
+            pp3.handle.close()
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -368,7 +535,7 @@ def main():
         out = {
             "metric": METRIC, "value": gdofs, "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {total_dofs} DOF, {m.n_elems} elements, "
+            "config": {"workload": f"{args.workload}: {'Tet10' if et == 10 else 'Hex8'} matrix-free K.u, {total_dofs} DOF, {total_elems} elements, "
                                    f"linear elastic E=210e9 nu=0.3, clamp x=0, deterministic scatter",
                        "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
                        "patch_elems": int(info.patch_elems), "n_patches": int(info.n_patches), "affine_elems": int(info.n_affine_elems), "smem_bytes": int(info.smem_bytes), "blocks_per_sm": int(info.blocks_per_sm), "interface_nodes": int(info.n_interface_nodes),
@@ -376,15 +543,21 @@ def main():
                                      + ("ncclSend/ncclRecv" if args.nccl_halo else "peer-memory stores over NVLink (CUDA IPC) issued from inside the patch kernel; "
                                         "patches that read ghost values run last and wait for the neighbours' flags")) if world > 1 else "single GPU",
                        "ms_min": float(times.min()), "ms_max": float(times.max()), "setup_s": float(info.setup_seconds),
-                       "launch": "one CUDA graph replay of the K timed steps" if use_graph else "per-step host launches",
-                       "host_enqueue_ms_per_step": None if host_s is None else host_s * 1e3,
-                       "per_rank_ms_mean_min_median_max": per_rank, "rank0_first_steps_ms": [round(float(v), 4) for v in times[:16]]},
+                       "launch": "one CUDA graph replay of the K timed steps" if tinfo["use_graph"] else "per-step host launches",
+                       "host_enqueue_ms_per_step": None if tinfo["host_s"] is None else tinfo["host_s"] * 1e3,
+                       "per_rank_ms_mean_min_median_max": per_rank, "rank0_first_steps_ms": [round(float(v), 4) for v in times[:16]],
+                       "host_threads": host_threads()},
+            "parity": parity,
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
                     "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},
-            "gpu_launches": launches_timed,
+            "gpu_launches": tinfo["launches"],
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_per_dof": BYTES_PER_DOF[et],
                          "note": "achieved = algorithmic bytes of one K.u / CUDA-event time of the whole step (patch kernel + interface reduce)"},
+            "fp64": {"tflops": FP64_FLOP_PER_ELEM[et] * total_elems / world / (ms * 1e-3) / 1e12,
+                     "flop_per_element": FP64_FLOP_PER_ELEM[et],
+                     "note": "fp64 instructions of the closed-form element kernel (SASS count, DFMA = 2 flop) per GPU; measured DFMA peak of the "
+                             "pipe: 64 lanes/clk/SM = 37.2 TFLOP/s at 1965 MHz (profiles/microbench/fp64_pipe.cu)"},
             "clocks": clocks,
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -395,8 +568,12 @@ def main():
                 pass
         if cg_out is not None:
             out["cg_time_to_solve"] = cg_out
-        if world == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(args.workload)
+        if asm_out is not None:
+            out["assembly"] = asm_out
+        if hex_out is not None:
+            out["hex8_weak"] = hex_out
+        if world == 1 and do_cpu:
+            out["cpu_baseline"] = cpu_baseline(args.workload, threads=host_threads())
         print(json.dumps(out), flush=True)
     h.close()
     if world > 1:

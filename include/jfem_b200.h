@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define JFEM_ABI_VERSION 1
+#define JFEM_ABI_VERSION 2
 
 /* status codes */
 #define JFEM_OK 0
@@ -51,6 +51,18 @@ extern "C" {
 #define JFEM_MAT_LINEAR_ELASTIC 0 /* params: E, nu */
 #define JFEM_MAT_NEO_HOOKEAN 1    /* params: E, nu  (mu, lambda derived as neo_hookean.jl:87-100); implies finite strain */
 #define JFEM_MAT_PERFECT_PLASTICITY 2 /* params: E, nu, sigma_y, H ; 13 state doubles per Gauss point */
+#define JFEM_MAT_STVK 3           /* params: E, nu.  St. Venant-Kirchhoff: Hooke's D on the Green-Lagrange strain = the classic
+                                     Problem(Elasticity) path with props.finite_strain = true (pe:255-332); the geometric
+                                     stiffness Kg (pe:378-404) enters the tangent only with option "geometric_stiffness" = 1 */
+
+/* surface element types of jfem_surface_load = nodes per face (Tri3, Quad4, Tri6; the Elasticity3DSurfaceElements of pe:454-458) */
+#define JFEM_TRI3 3
+#define JFEM_QUAD4 4
+#define JFEM_TRI6 6
+
+/* jfem_nodal_recover fields (pe:520-545) */
+#define JFEM_FIELD_STRAIN 0 /* 11, 22, 33, 12, 23, 13 (tensor shear components) */
+#define JFEM_FIELD_STRESS 1 /* linear-elastic stress of the small strain, same order */
 
 /* jfem_matvec / jfem_cg flags */
 #define JFEM_PROJECT 1      /* zero Dirichlet rows of the result (apply_dirichlet_kernel!, ext:423-435) */
@@ -89,6 +101,7 @@ int jfem_destroy(jfem_handle *h);
  * "warp_specialised" (1/0), "lane_window" (candidates per lane of the bank-aware lane assignment, 0 = off),
  * "fused_halo" (1: halo exchange inside the patch kernel when peer mappings exist [default]),
  * "fused_interface" (1: cooperative-launch in-kernel interface reduction; default 0, measured slower),
+ * "geometric_stiffness" (props.geometric_stiffness of pe:36-46 for JFEM_MAT_STVK; default 0),
  * profiling aids "debug_timing", "debug_skip" */
 int jfem_set_option(jfem_handle *h, const char *key, double value);
 /* homogeneous material (per_element == 0: params has n_params entries, 2 <= n_params <= 4) or per-element
@@ -123,6 +136,33 @@ int jfem_csr_pattern(jfem_handle *h, int64_t *rowptr, int32_t *colind);
  * symmetrise != 0 applies K <- (K+K')/2 (src/solvers.jl:289-292) */
 int jfem_assemble_csr(jfem_handle *h, const double *u, double *vals, double *f_int, int symmetrise, int on_device);
 int jfem_spmv(jfem_handle *h, const double *x, double *y, int flags, int on_device);
+
+/* Penalty Dirichlet conditions on the assembled operator, the CPU backend's apply_dirichlet_bc! (eas:237-252): for every
+ * fixed dof i  K[i,i] += penalty, r[i] = penalty * prescribed[i]  with penalty = scale * max|K| (the reference uses
+ * scale = 1e10).  Works on the handle's device CSR (after jfem_assemble_csr); rhs: n_dofs vector, modified in place
+ * (may be NULL); *penalty_out returns the value used. */
+int jfem_csr_penalty_bc(jfem_handle *h, double scale, double *rhs, double *penalty_out, int on_device);
+
+/* --- external loads: replaces the f_ext part of assemble_element! (pe:412-426) and the surface assembly
+ *     assemble!(..., Elasticity3DSurfaceElements) (pe:454-502; GPU precedent apply_surface_traction_kernel!, ext:368-416).
+ *     Consistent integration with the reference's default rules (GLTET4 / GLHEX8 / GLTET1; GLTRI1 / GLTRI3 / GLQUAD4),
+ *     one thread per node summing its incident elements / faces in ascending order: deterministic, no atomics. */
+/* f (+)= sum_e sum_gp w detJ N b.  b: 3 values ("displacement load 1..3"), or 3 x n_elems column-major if per_element */
+int jfem_body_load(jfem_handle *h, const double *b, int per_element, int accumulate, double *f, int on_device);
+/* faces: face_type x n_faces column-major node ids of the VOLUME mesh (index_base-based), reference node order.
+ * traction: 3 x n_faces ("displacement traction force", may be NULL); pressure: n_faces ("surface pressure": positive
+ * pressure acts against the face normal n = dX/dxi1 x dX/dxi2, pe:485-491; may be NULL).  host arrays. */
+int jfem_surface_load(jfem_handle *h, int face_type, int64_t n_faces, const int32_t *faces, const double *traction,
+                      const double *pressure, int accumulate, double *f, int on_device);
+/* reaction forces of the constrained dofs, la = f_int(u) - f_ext there and 0 elsewhere: what solve! returns as the
+ * Lagrange multipliers of the eliminated boundary rows (src/solvers.jl:205-216) */
+int jfem_reactions(jfem_handle *h, const double *u, const double *f_ext, double *la, int on_device);
+
+/* --- post-processing: replaces postprocess!(problem, time, Val{:strain|:stress}) -> lsq_fit (pe:547-594):
+ *     least-squares fit of the Gauss-point field to the nodes, M x = b with M = sum w detJ N N', b_i = sum w detJ f_i N,
+ *     M assembled on the node adjacency pattern (coloured, deterministic) and solved by Jacobi-PCG to 1e-14 (the reference
+ *     factorises M).  out: 6 x n_nodes column-major. */
+int jfem_nodal_recover(jfem_handle *h, const double *u, int field, double *out, int on_device);
 
 /* --- solvers: replaces cg_solve_matfree_gpu! (ext:531-577) / cg_solve (cpu:221-254) and
  *     solve_newton_krylov_gpu! (ext:685-854) --------------------------------------------------- */

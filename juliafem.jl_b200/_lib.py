@@ -14,7 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjfem_b200.so")
 
 TET4, HEX8, TET10 = 4, 8, 10
-MAT_LINEAR_ELASTIC, MAT_NEO_HOOKEAN, MAT_PERFECT_PLASTICITY = 0, 1, 2
+MAT_LINEAR_ELASTIC, MAT_NEO_HOOKEAN, MAT_PERFECT_PLASTICITY, MAT_STVK = 0, 1, 2, 3
+FIELD_STRAIN, FIELD_STRESS = 0, 1
+TRI3, QUAD4, TRI6 = 3, 4, 6
 PROJECT, TANGENT, USE_CSR, JACOBI = 1, 2, 4, 8
 NSTATE = 13
 NGP = {4: 1, 8: 8, 10: 4}
@@ -25,7 +27,8 @@ EXPORTS = [
     "jfem_internal_force", "jfem_set_linearization", "jfem_commit_state", "jfem_get_state", "jfem_set_state",
     "jfem_element_matrices", "jfem_csr_size", "jfem_csr_pattern", "jfem_assemble_csr", "jfem_spmv", "jfem_cg",
     "jfem_newton_krylov", "jfem_comm_unique_id", "jfem_comm_init", "jfem_comm_set_halo", "jfem_comm_p2p_export",
-    "jfem_comm_p2p_import", "jfem_comm_p2p_seq", "jfem_comm_destroy",
+    "jfem_comm_p2p_import", "jfem_comm_p2p_seq", "jfem_comm_destroy", "jfem_body_load", "jfem_surface_load", "jfem_reactions",
+    "jfem_nodal_recover", "jfem_csr_penalty_bc",
 ]
 
 
@@ -92,6 +95,11 @@ def lib():
         L.jfem_comm_p2p_import.argtypes = [vp, C.c_char_p, vp, vp]
         L.jfem_comm_p2p_seq.argtypes = [vp, i64, C.POINTER(i64)]
         L.jfem_comm_destroy.argtypes = [vp]
+        L.jfem_body_load.argtypes = [vp, vp, i32, i32, vp, i32]
+        L.jfem_surface_load.argtypes = [vp, i32, i64, vp, vp, vp, i32, vp, i32]
+        L.jfem_reactions.argtypes = [vp, vp, vp, vp, i32]
+        L.jfem_nodal_recover.argtypes = [vp, vp, i32, vp, i32]
+        L.jfem_csr_penalty_bc.argtypes = [vp, dbl, vp, C.POINTER(dbl), i32]
         for name in EXPORTS:
             if name != "jfem_last_error":
                 getattr(L, name).restype = i32
@@ -254,6 +262,51 @@ class Handle:
         check(lib().jfem_assemble_csr(self._h, pu, None if vals is None else vals.ctypes.data_as(C.c_void_p),
                                       None if f is None else f.ctypes.data_as(C.c_void_p), int(symmetrise), 0))
         return vals, f
+
+    # ---- loads, reactions, post-processing (host arrays)
+    def body_load(self, b, f=None):
+        """f (+)= consistent body load; b = 3 values or (n_elems, 3).  f given -> accumulated into a copy of it."""
+        bb = np.ascontiguousarray(b, dtype=np.float64)
+        per = int(bb.ndim == 2)
+        if per:
+            assert bb.shape == (self.n_elems, 3)
+        out = np.zeros(self.n_dofs) if f is None else np.array(f, dtype=np.float64)
+        check(lib().jfem_body_load(self._h, bb.ctypes.data_as(C.c_void_p), per, int(f is not None), out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def surface_load(self, face_type, faces, traction=None, pressure=None, f=None):
+        """Consistent surface traction (3 values or (n_faces, 3)) / pressure (scalar or (n_faces,)) on faces given by
+        volume-mesh node ids (n_faces, face_type)."""
+        fc = np.ascontiguousarray(faces, dtype=np.int32).reshape(-1, face_type)
+        nf = fc.shape[0]
+        t = None if traction is None else np.ascontiguousarray(np.broadcast_to(np.asarray(traction, dtype=np.float64), (nf, 3)))
+        p = None if pressure is None else np.ascontiguousarray(np.broadcast_to(np.asarray(pressure, dtype=np.float64), (nf,)))
+        out = np.zeros(self.n_dofs) if f is None else np.array(f, dtype=np.float64)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        check(lib().jfem_surface_load(self._h, face_type, nf, vp(fc), vp(t), vp(p), int(f is not None), vp(out), 0))
+        return out
+
+    def reactions(self, u, f_ext=None):
+        uu = np.ascontiguousarray(u, dtype=np.float64)
+        fe = None if f_ext is None else np.ascontiguousarray(f_ext, dtype=np.float64)
+        la = np.zeros(self.n_dofs)
+        check(lib().jfem_reactions(self._h, uu.ctypes.data_as(C.c_void_p), None if fe is None else fe.ctypes.data_as(C.c_void_p),
+                                   la.ctypes.data_as(C.c_void_p), 0))
+        return la
+
+    def nodal_recover(self, u, field=FIELD_STRESS):
+        """(n_nodes, 6) least-squares nodal fit of the Gauss-point strain / stress, order 11 22 33 12 23 13."""
+        uu = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.zeros((self.n_nodes, 6))
+        check(lib().jfem_nodal_recover(self._h, uu.ctypes.data_as(C.c_void_p), field, out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    def csr_penalty_bc(self, rhs=None, scale=1e10):
+        """apply_dirichlet_bc! of the reference's CPU backend on the handle's assembled CSR; returns (penalty, rhs)."""
+        r = None if rhs is None else np.array(rhs, dtype=np.float64)
+        pen = C.c_double(0.0)
+        check(lib().jfem_csr_penalty_bc(self._h, scale, None if r is None else r.ctypes.data_as(C.c_void_p), C.byref(pen), 0))
+        return pen.value, r
 
     def cg(self, b, x0=None, tol=1e-6, relative=False, max_iter=1000, flags=0):
         pb, db, kb = _ptr(b, self.n_dofs)

@@ -28,6 +28,7 @@ from . import _lib
 Tet4, Hex8, Tet10, Tri3, Tri6, Quad4, Poi1 = "Tet4", "Hex8", "Tet10", "Tri3", "Tri6", "Quad4", "Poi1"
 _NNPE = {Tet4: 4, Hex8: 8, Tet10: 10, Tri3: 3, Tri6: 6, Quad4: 4, Poi1: 1}
 _VOLUME = (Tet4, Hex8, Tet10)
+_SURFACE = (Tri3, Tri6, Quad4)
 
 
 class Elasticity:
@@ -194,7 +195,9 @@ def _material_of(elements, properties, explicit=None):
     nu = {_get(el, "poissons ratio", "poissons_ratio") for el in elements}
     if None in E or None in nu:
         raise KeyError("elements need \"youngs modulus\" and \"poissons ratio\" fields")   # reference: KeyError from element(...)
-    kind = _lib.MAT_NEO_HOOKEAN if getattr(properties, "finite_strain", False) else _lib.MAT_LINEAR_ELASTIC
+    # props.finite_strain of the classic path = Hooke's D on the Green-Lagrange strain (St. Venant-Kirchhoff,
+    # src/problems_elasticity.jl:255-332); Neo-Hookean only when a NeoHookean material is given explicitly
+    kind = _lib.MAT_STVK if getattr(properties, "finite_strain", False) else _lib.MAT_LINEAR_ELASTIC
     if len(E) != 1 or len(nu) != 1:      # per-element arrays, like E_vec / nu_vec of ext/JuliaFEMCUDAExt.jl:135-141
         return kind, np.array([[_get(el, "youngs modulus", "youngs_modulus"), _get(el, "poissons ratio", "poissons_ratio")] for el in elements])
     return kind, (E.pop(), nu.pop())
@@ -207,10 +210,11 @@ class ElasticityDataGPU:
         vol = [el for el in elements if el.topology in _VOLUME]
         if not vol:
             raise ValueError("no volume elements")
-        bad = [el for el in elements if el.topology not in _VOLUME]
+        bad = [el for el in elements if el.topology not in _VOLUME and el.topology not in _SURFACE]
         if bad:
             # same refusal as assemble! for e.g. Seg3 in a 3D problem (src/problems_elasticity.jl:510-518)
             raise ValueError(f"unsupported element type {bad[0].topology} in a 3D continuum problem")
+        self.surface_elements = [el for el in elements if el.topology in _SURFACE]   # Elasticity3DSurfaceElements (pe:454-458)
         kinds = {el.topology for el in vol}
         if len(kinds) != 1:
             raise NotImplementedError("one element type per problem on the accelerated path")
@@ -232,6 +236,8 @@ class ElasticityDataGPU:
         for k, v in (options or {}).items():
             self.handle.set_option(k, v)
         self.handle.set_material(*_material_of(vol, properties, material))
+        if getattr(properties, "geometric_stiffness", False):
+            self.handle.set_option("geometric_stiffness", 1)
         # Dirichlet: is_fixed / prescribed per dof (ext:144-158)
         dofs, vals = [], []
         for nodes, comps, val in zip(dirichlet.node_ids, dirichlet.components, dirichlet.values):
@@ -244,52 +250,40 @@ class ElasticityDataGPU:
         if dofs:
             self.prescribed[self.fixed_dofs - 1] = vals
         self.handle.set_dirichlet(self.fixed_dofs, np.array(vals))
-        # external load: Tri3 lumped traction area/3 * t exactly as apply_surface_traction_kernel! (ext:368-416)
+        # external loads, integrated on the device (jfem_surface_load / jfem_body_load):
+        #  * Neumann surfaces of seam 1: consistent traction; for Tri3 (GLTRI1) this IS the lumped area/3 * t of
+        #    apply_surface_traction_kernel! (ext:368-416)
+        #  * surface elements of the classic problem with "displacement traction force [i]" / "surface pressure" (pe:454-502)
+        #  * "displacement load [i]" body loads of the volume elements (pe:412-426)
+        self.remap = remap
         self.f_ext = np.zeros(self.n_dofs)
+        groups = {}
         for surf, t in zip(neumann.surface_elements, neumann.traction):
-            self.f_ext += surface_traction(surf, t, remap, self.n_dofs)
+            groups.setdefault(surf.topology, []).append((surf, np.asarray(t, dtype=np.float64), None))
+        for surf in self.surface_elements:
+            t = _get(surf, "displacement traction force")
+            t = np.zeros(3) if t is None else np.asarray(t, dtype=np.float64).copy()
+            for i in range(3):
+                ti = _get(surf, f"displacement traction force {i + 1}")
+                if ti is not None:
+                    t[i] += float(ti)
+            groups.setdefault(surf.topology, []).append((surf, t, _get(surf, "surface pressure")))
+        for topo, items in groups.items():
+            faces = np.array([[remap[int(n)] for n in sf.connectivity] for sf, _, _ in items], dtype=np.int32)
+            trac = np.array([t for _, t, _ in items])
+            pres = np.array([0.0 if p is None else float(p) for _, _, p in items])
+            self.f_ext = self.handle.surface_load(_NNPE[topo], faces, traction=trac if np.any(trac) else None,
+                                                  pressure=pres if np.any(pres) else None, f=self.f_ext)
+        b = np.array([[float(_get(el, f"displacement load {i + 1}", default=0.0)) for i in range(3)] for el in vol])
+        for k, el in enumerate(vol):
+            bv = _get(el, "displacement load")
+            if bv is not None:
+                b[k] += np.asarray(bv, dtype=np.float64)
+        if np.any(b):
+            self.f_ext = self.handle.body_load(b[0] if np.all(b == b[0]) else b, f=self.f_ext)
 
     def close(self):
         self.handle.close()
-
-
-def surface_traction(surf: Element, traction, remap, n_dofs):
-    """Nodal forces of a constant traction on one surface element.  Tri3: lumped area/3 (the reference's GPU kernel,
-    ext/JuliaFEMCUDAExt.jl:368-416); Tri6 / Quad4: consistent (src/problems_elasticity.jl:454-502)."""
-    f = np.zeros(n_dofs)
-    X = np.asarray(_get(surf, "geometry"), dtype=np.float64)
-    nn = _NNPE[surf.topology]
-    X = _nodes_by_rows(X, nn)
-    ids = [remap[int(n)] for n in surf.connectivity]
-    t = np.asarray(traction, dtype=np.float64)
-    if surf.topology == Tri3:
-        area = 0.5 * np.linalg.norm(np.cross(X[1] - X[0], X[2] - X[0]))
-        w = np.full(3, area / 3.0)
-    elif surf.topology == Tri6:
-        # GLTRI3 (degree 2) on the quadratic triangle: consistent load
-        pts = [(1 / 6, 1 / 6), (2 / 3, 1 / 6), (1 / 6, 2 / 3)]
-        w = np.zeros(6)
-        for u, v in pts:
-            L = 1 - u - v
-            N = np.array([L * (2 * L - 1), u * (2 * u - 1), v * (2 * v - 1), 4 * L * u, 4 * u * v, 4 * v * L])
-            dNu = np.array([-(4 * L - 1), 4 * u - 1, 0, 4 * (L - u), 4 * v, -4 * v])
-            dNv = np.array([-(4 * L - 1), 0, 4 * v - 1, -4 * u, 4 * u, 4 * (L - v)])
-            w += N * np.linalg.norm(np.cross(dNu @ X, dNv @ X)) / 6.0
-    elif surf.topology == Quad4:
-        a = 0.5773502691896258
-        w = np.zeros(4)
-        s = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], float)
-        for u in (-a, a):
-            for v in (-a, a):
-                N = 0.25 * (1 + s[:, 0] * u) * (1 + s[:, 1] * v)
-                dNu = 0.25 * s[:, 0] * (1 + s[:, 1] * v)
-                dNv = 0.25 * s[:, 1] * (1 + s[:, 0] * u)
-                w += N * np.linalg.norm(np.cross(dNu @ X, dNv @ X))
-    else:
-        raise ValueError(f"unsupported surface element {surf.topology}")
-    for i, n in enumerate(ids):
-        f[3 * (n - 1):3 * n] += w[i] * t
-    return f
 
 
 def initialize_backend(backend, physics: Physics, time=0.0, options=None):
@@ -379,7 +373,32 @@ class Problem:
         self.elements: list = []
         self.assembly = Assembly()
         self.material = None
+        self.postprocess_fields: list = []
+        self.fields: dict = {}
         self._data = None
+
+    def postprocess(self, name):
+        """postprocess!(problem, time, Val{:strain|:stress})  (src/problems_elasticity.jl:583-594): least-squares nodal fit
+        of the Gauss-point field on the device; returns (and keeps in problem.fields[name]) {node id: 6-vector}."""
+        if name not in ("stress", "strain"):
+            raise KeyError(name)
+        if self._data is None or self.assembly.u is None:
+            raise RuntimeError("postprocess needs a solved problem")
+        d = self._data
+        x = d.handle.nodal_recover(self.assembly.u, _lib.FIELD_STRESS if name == "stress" else _lib.FIELD_STRAIN)
+        self.fields[name] = {int(n): x[i] for i, n in enumerate(d.node_ids)}
+        return self.fields[name]
+
+
+def apply_dirichlet_bc_(problem: "Problem", rhs=None, scale=1e10):
+    """apply_dirichlet_bc!(assembly, fixed_dofs, prescribed) of the CPU backend (src/element_assembly_structures.jl:237-252):
+    penalty = scale * max|K| added to the diagonal of every fixed dof of the ASSEMBLED K (on the device),
+    rhs[dof] = penalty * prescribed.  Returns (penalty, rhs)."""
+    d = problem._data
+    if d is None or problem.assembly.K is None:
+        raise RuntimeError("apply_dirichlet_bc_ needs an assembled problem (assemble_)")
+    pen, r = d.handle.csr_penalty_bc(problem.assembly.f if rhs is None else rhs, scale)
+    return pen, r
 
 
 def _dirichlet_from(problems):
@@ -397,66 +416,19 @@ def _dirichlet_from(problems):
     return bc
 
 
-def _body_load(data: ElasticityDataGPU, elements):
-    """f_ext += w N b for "displacement load i" fields (src/problems_elasticity.jl:412-426), host-side numpy."""
-    f = np.zeros(data.n_dofs)
-    loads = [(i, {_get(el, f"displacement load {i + 1}") for el in elements}) for i in range(3)]
-    loads = [(i, v.pop()) for i, v in loads if len(v) == 1 and None not in v]
-    if not loads:
-        return f
-    nn = data.conn.shape[1]
-    if nn == 10:
-        a, b = (5 + 3 * np.sqrt(5.0)) / 20, (5 - np.sqrt(5.0)) / 20
-        pts, wts = np.array([[a, b, b], [b, a, b], [b, b, a], [b, b, b]]), np.full(4, 1 / 24)
-    elif nn == 4:
-        pts, wts = np.array([[0.25, 0.25, 0.25]]), np.array([1 / 6])
-    else:
-        g = 0.5773502691896258
-        pts = np.array([[i, j, k] for k in (-g, g) for j in (-g, g) for i in (-g, g)])
-        wts = np.ones(8)
-    X = data.coords[data.conn - 1]                                   # (ne, nn, 3)
-    for xi, w in zip(pts, wts):
-        N, dN = _shape(nn, xi)
-        J = np.einsum("ia,eib->eab", dN, X)
-        wd = w * np.linalg.det(J)
-        for comp, bval in loads:
-            np.add.at(f, 3 * (data.conn - 1) + comp, wd[:, None] * N[None, :] * bval)
-    return f
-
-
-def _shape(nn, xi):
-    u, v, w = xi
-    if nn == 4:
-        N = np.array([1 - u - v - w, u, v, w])
-        dN = np.array([[-1, -1, -1], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
-    elif nn == 10:
-        L = 1 - u - v - w
-        N = np.array([L * (2 * L - 1), u * (2 * u - 1), v * (2 * v - 1), w * (2 * w - 1), 4 * L * u, 4 * u * v, 4 * L * v, 4 * L * w, 4 * u * w, 4 * v * w])
-        d = 1 - 4 * L
-        dN = np.array([[d, d, d], [4 * u - 1, 0, 0], [0, 4 * v - 1, 0], [0, 0, 4 * w - 1], [4 * (L - u), -4 * u, -4 * u], [4 * v, 4 * u, 0],
-                       [-4 * v, 4 * (L - v), -4 * v], [-4 * w, -4 * w, 4 * (L - w)], [4 * w, 0, 4 * u], [0, 4 * w, 4 * v]])
-    else:
-        s = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1], [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], float)
-        N = 0.125 * (1 + s[:, 0] * u) * (1 + s[:, 1] * v) * (1 + s[:, 2] * w)
-        dN = 0.125 * np.stack([s[:, 0] * (1 + s[:, 1] * v) * (1 + s[:, 2] * w), s[:, 1] * (1 + s[:, 0] * u) * (1 + s[:, 2] * w),
-                               s[:, 2] * (1 + s[:, 0] * u) * (1 + s[:, 1] * v)], axis=1)
-    return N, dN
-
-
 def _ensure_data(problem: Problem, boundary=(), device=0):
     if problem._data is None:
         problem._data = ElasticityDataGPU(problem.elements, _dirichlet_from(boundary), NeumannBC(), problem.properties,
                                           material=problem.material, device=device)
-        problem._data.f_ext += _body_load(problem._data, problem.elements)
     return problem._data
 
 
-def assemble_(problem: Problem, time=0.0, u=None, symmetrise=False, device=0):
+def assemble_(problem: Problem, time=0.0, u=None, symmetrise=False, device=0, boundary=()):
     """assemble!(problem, time)  (src/assembly/assembly.jl:31): leaves K (assembled on the GPU: element integration +
     coloured scatter into the reference's sparsity pattern) and f = f_ext - f_int in problem.assembly."""
     if isinstance(problem.properties, Dirichlet):
         return problem                      # boundary problems only contribute their dof lists (handled by the solver)
-    d = _ensure_data(problem, device=device)
+    d = _ensure_data(problem, boundary, device=device)     # boundary: Dirichlet problems (only needed by apply_dirichlet_bc_)
     rowptr, colind = d.handle.csr_pattern()
     vals, fint = d.handle.assemble_csr(u, symmetrise=symmetrise, want_f=u is not None)
     problem.assembly.K = SparseMatrixCSR(rowptr, colind, vals, d.n_dofs)
@@ -527,7 +499,7 @@ def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0,
         scale = _free_norm(d.f_ext - (h.matvec(d.prescribed) if np.any(d.prescribed) else 0.0), d.fixed_dofs)
         rel = max(tol, 1e-10) if newton_tol is None else newton_tol
         ntol = rel * (scale if scale > 0 else 1.0)
-        max_newton = max(20, getattr(analysis.properties, "max_iterations", 10))
+        max_newton = analysis.properties.max_iterations if isinstance(analysis.properties, Nonlinear) else 20   # src/solvers.jl:539-551
         u, nit, cgit, res, hist = h.newton_krylov(d.f_ext, d.prescribed.copy(), newton_tol=ntol, max_newton=max_newton,
                                                   max_cg_per_newton=max_iter, forcing_max=1e-3)
         analysis.iterations, analysis.cg_iterations, analysis.history = nit, cgit, hist
@@ -538,7 +510,6 @@ def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0,
                 analysis.u, analysis.residual = u, res
                 raise ConvergenceError(msg)
             warnings.warn(msg)
-        fint = h.internal_force(u)
     else:
         b = d.f_ext - (h.matvec(d.prescribed) if np.any(d.prescribed) else 0.0)
         x, it, res = h.cg(b, tol=tol, relative=relative, max_iter=max_iter)
@@ -548,15 +519,14 @@ def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0,
         analysis.converged = bool(res <= thr if relative else res < thr)
         if not analysis.converged:
             warnings.warn(f"CG did not converge in {it} iterations: ||r|| = {res:.3e} > {thr:.3e}")
-        fint = h.matvec(u)
     analysis.residual = res
     analysis.u = u
-    # reaction forces on the constrained dofs: la = K u - f (src/solvers.jl:211-216), zero elsewhere
-    analysis.reactions = np.zeros(d.n_dofs)
-    if d.fixed_dofs.size:
-        analysis.reactions[d.fixed_dofs - 1] = (fint - d.f_ext)[d.fixed_dofs - 1]
+    # reaction forces on the constrained dofs: la = f_int(u) - f_ext (src/solvers.jl:211-216), zero elsewhere
+    analysis.reactions = h.reactions(u, d.f_ext)
     model.assembly.u = u
     model.assembly.la = analysis.reactions
+    for name in model.postprocess_fields:          # push!(model.postprocess_fields, "stress")  (examples/linear_static.jl:96)
+        model.postprocess(name)
     return analysis
 
 

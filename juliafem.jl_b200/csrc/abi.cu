@@ -110,7 +110,7 @@ int jfem_destroy(jfem_handle *h) {
     h->nk_f.release(); h->red_partials.release(); h->cg_s.release(); h->nadj_ptr.release(); h->rowptr.release(); h->nadj.release();
     h->colind.release(); h->vals.release(); h->eblk.release(); h->dconn.release(); h->colour_elems.release(); h->e2i.release();
     h->send_nodes.release(); h->recv_nodes.release(); h->send_buf.release(); h->recv_buf.release();
-    h->timing.release(); h->xal.release(); h->cg_s.release();
+    h->timing.release(); h->xal.release(); h->cg_s.release(); h->n2e_ptr.release(); h->n2e_inc.release();
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return JFEM_OK;
@@ -134,6 +134,8 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         h->fused_halo = value != 0;
     } else if (!strcmp(key, "fused_interface")) {
         h->fused_iface = value != 0;
+    } else if (!strcmp(key, "geometric_stiffness")) {
+        h->geometric_stiffness = value != 0;
     } else if (!strcmp(key, "debug_skip")) {
         h->debug_skip = (int)value;
     } else if (!strcmp(key, "lane_window")) {
@@ -156,7 +158,7 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
 int jfem_set_material(jfem_handle *h, int kind, const double *params, int n_params, int per_element) {
     CHECK_H(h);
     const int need = kind == JFEM_MAT_PERFECT_PLASTICITY ? 4 : 2;
-    if (kind < 0 || kind > 2 || !params || n_params < need || n_params > 4) { jfem_set_error("jfem_set_material: bad kind/params"); return JFEM_EINVAL; }
+    if (kind < 0 || kind > JFEM_MAT_STVK || !params || n_params < need || n_params > 4) { jfem_set_error("jfem_set_material: bad kind/params"); return JFEM_EINVAL; }
     const int64_t nsets = per_element ? h->mesh.n_elems : 1;
     for (int64_t e = 0; e < nsets; e++) {
         const double *q = params + e * n_params;

@@ -267,6 +267,7 @@ static int columns_by_material(jfem_handle *h, AsmArgs a) {
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
     if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; fill_material(h, pt); return launch_columns<NNPE>(h, a, pt); }
     if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; fill_material(h, pt); return launch_columns<NNPE>(h, a, pt); }
+    if (h->mat_kind == JFEM_MAT_STVK) { PtStVKTangent pt; fill_material(h, pt); pt.geo = h->geometric_stiffness ? 1 : 0; return launch_columns<NNPE>(h, a, pt); }
     if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY) {
         PtPPTangent pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.n_gp = n_gp;
         return launch_columns<NNPE>(h, a, pt);
@@ -334,6 +335,7 @@ static int fint_by_material(jfem_handle *h, AsmArgs a, double *fe) {
     const unsigned blocks = (unsigned)((a.ne + 127) / 128);
     if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC) { PtLinear pt; fill_material(h, pt); elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
     else if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHResidual pt; fill_material(h, pt); elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
+    else if (h->mat_kind == JFEM_MAT_STVK) { PtStVKResidual pt; fill_material(h, pt); pt.geo = 0; elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe); }
     else {
         PtPPResidual pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.st_new = nullptr; pt.n_gp = n_gp;
         elem_fint_kernel<NNPE><<<blocks, 128, 0, h->stream>>>(a, pt, fe);
@@ -418,6 +420,7 @@ static int diag_by_material(jfem_handle *h, AsmArgs a, double *D, bool tangent) 
     const long long n_gp = (long long)h->mesh.n_elems * h->ngp();
     if (h->mat_kind == JFEM_MAT_LINEAR_ELASTIC || !tangent) { PtLinear pt; fill_material(h, pt); return launch_diag<NNPE>(h, a, pt, D); }
     if (h->mat_kind == JFEM_MAT_NEO_HOOKEAN) { PtNHTangent pt; fill_material(h, pt); return launch_diag<NNPE>(h, a, pt, D); }
+    if (h->mat_kind == JFEM_MAT_STVK) { PtStVKTangent pt; fill_material(h, pt); pt.geo = h->geometric_stiffness ? 1 : 0; return launch_diag<NNPE>(h, a, pt, D); }
     PtPPTangent pt; fill_material(h, pt); pt.st_old = h->st_old.p; pt.n_gp = n_gp;
     return launch_diag<NNPE>(h, a, pt, D);
 }

@@ -139,6 +139,49 @@ struct PtNHTangent : NHCommon {   // field 0 = v (direction), field 1 = u (linea
     }
 };
 
+// St. Venant-Kirchhoff = the reference's classic finite-strain path (props.finite_strain = true, src/problems_elasticity.jl:
+// 255-332): Hooke's D applied to the Green-Lagrange strain E = 1/2 (grad u + grad u' + grad u' grad u), S = la tr(E) I + 2 mu E,
+// Total Lagrangian P = F S.  Tangent: dP = F (D : sym(F' dF))  [BL' D BL, :270-289,370-375]  (+ dF S, the geometric
+// stiffness Kg of :378-404, only when props.geometric_stiffness is set -- `geo`).
+struct StVKCommon : MatBase {
+    int geo;
+    JF_HD void kin(const double (&Gu)[3][3], double (&F)[3][3], double (&S)[3][3]) const {
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) F[i][j] = Gu[i][j] + (i == j ? 1.0 : 0.0);
+        double E[3][3];
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++)
+            E[i][j] = 0.5 * (Gu[i][j] + Gu[j][i] + Gu[0][i] * Gu[0][j] + Gu[1][i] * Gu[1][j] + Gu[2][i] * Gu[2][j]);
+        const double tr = la * (E[0][0] + E[1][1] + E[2][2]);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) S[i][j] = 2.0 * mu * E[i][j] + (i == j ? tr : 0.0);
+    }
+};
+
+struct PtStVKResidual : StVKCommon {
+    static constexpr int NF = 1;
+    JF_HD bool eval(long long, const double (&G)[1][3][3], double (&P)[3][3]) const {
+        double F[3][3], S[3][3];
+        kin(G[0], F, S);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) P[i][j] = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
+        return true;
+    }
+};
+
+struct PtStVKTangent : StVKCommon {   // field 0 = v (direction), field 1 = u (linearisation point)
+    static constexpr int NF = 2;
+    JF_HD bool eval(long long, const double (&G)[2][3][3], double (&P)[3][3]) const {
+        double F[3][3], S[3][3], A[3][3], dS[3][3];
+        kin(G[1], F, S);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) A[i][j] = F[0][i] * G[0][0][j] + F[1][i] * G[0][1][j] + F[2][i] * G[0][2][j];
+        const double tr = la * (A[0][0] + A[1][1] + A[2][2]);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) dS[i][j] = mu * (A[i][j] + A[j][i]) + (i == j ? tr : 0.0);
+        JF_UNROLL for (int i = 0; i < 3; i++) JF_UNROLL for (int j = 0; j < 3; j++) {
+            double v = F[i][0] * dS[0][j] + F[i][1] * dS[1][j] + F[i][2] * dS[2][j];
+            if (geo) v += G[0][i][0] * S[0][j] + G[0][i][1] * S[1][j] + G[0][i][2] * S[2][j];
+            P[i][j] = v;
+        }
+        return true;
+    }
+};
+
 // J2 plasticity with linear kinematic hardening, radial return (src/materials/perfect_plasticity.jl:247-341).
 // State per Gauss point, SoA: st[s * n_gp + gp], s = 0..12 (eps_p 11,22,33,12,23,13 ; alpha ; kappa).
 struct PPCommon : MatBase {

@@ -22,6 +22,7 @@ struct jfem_handle {
     // options
     int patch_elems = 256;
     bool deterministic = true, affine = true, warp_specialised = true;
+    bool geometric_stiffness = false;   // option "geometric_stiffness": Kg in the St. Venant-Kirchhoff tangent (pe:378-404)
     int debug_skip = 0;                 // profiling aid (option "debug_skip"): phases of the ws kernel to leave out
     int lane_window = 48;               // candidates examined per lane by the bank-aware lane assignment (0 = off)
     // material
@@ -71,6 +72,7 @@ struct jfem_handle {
     DevBuf<int32_t> colour_elems;       // elements sorted by colour
     std::vector<int64_t> colour_ptr;
     DevBuf<int64_t> e2i;                // caller element -> internal element index (state lookup)
+    DevBuf<long long> n2e_ptr, n2e_inc; // node -> (element * nnpe + local node) incidences, ascending (loads.cu)
     bool vals_valid = false;
     // comm
     ncclComm *comm = nullptr;

@@ -762,6 +762,11 @@ static int dispatch_mode(jfem_handle *h, const PatchSetDev &D, PatchKArgs a, int
         PtNHTangent pt; fill_material(h, pt);
         return launch_set<NNPE, CLASS_GENERAL, OP_TANGENT, PtNHTangent, T>(h, D, a, pt);
     }
+    if (h->mat_kind == JFEM_MAT_STVK) {
+        if (mode == OP_RESIDUAL) { PtStVKResidual pt; fill_material(h, pt); pt.geo = 0; return launch_set<NNPE, CLASS_GENERAL, OP_RESIDUAL, PtStVKResidual, T>(h, D, a, pt); }
+        PtStVKTangent pt; fill_material(h, pt); pt.geo = h->geometric_stiffness ? 1 : 0;
+        return launch_set<NNPE, CLASS_GENERAL, OP_TANGENT, PtStVKTangent, T>(h, D, a, pt);
+    }
     if (h->mat_kind == JFEM_MAT_PERFECT_PLASTICITY) {
         if (mode == OP_RESIDUAL) {
             PtPPResidual pt; fill_material(h, pt);

@@ -373,41 +373,91 @@ class Partition:
     recv: dict                  # neighbour rank -> local (1-based) ghost node ids to receive into, ascending global id
 
 
-def partition_mesh(mesh: Mesh, n_ranks: int, rank: int) -> Partition:
+def partition_mesh(mesh: Mesh, n_ranks: int, rank: int, node_offset: int = 0, n_nodes_global: int | None = None) -> Partition:
     """Owner-computes partition with one layer of ghost elements
     (benchmarks/multigpu_mpi_benchmark.jl:120-229): rank r owns the contiguous node-id range
     [r*ceil(nn/P)+1, min((r+1)*ceil(nn/P), nn)]; local elements = those touching >= 1 owned node;
     ghosts = their non-owned nodes, sorted ascending after the owned ones; rank r sends to s the
     owned nodes that appear in s's ghost list (i.e. owned nodes of elements that also touch
-    s-owned nodes)."""
-    nn = mesh.n_nodes
+    s-owned nodes).
+
+    `mesh` may be a WINDOW of a larger mesh (lattice_window): its node i+1 is global node i+1+node_offset of a mesh with
+    n_nodes_global nodes, and it must contain every element that touches a node owned by `rank`."""
+    nn = mesh.n_nodes if n_nodes_global is None else int(n_nodes_global)
     per = -(-nn // n_ranks)
     lo, hi = rank * per + 1, min((rank + 1) * per, nn)
-    owner = (mesh.conn.astype(np.int64) - 1) // per           # (ne, nnpe)
+    cg = mesh.conn.astype(np.int64) + node_offset             # global ids
+    owner = (cg - 1) // per                                   # (ne, nnpe)
     mine = (owner == rank).any(axis=1)
     elems = np.nonzero(mine)[0]
-    c = mesh.conn[elems].astype(np.int64)
+    c = cg[elems]
     touched = np.unique(c)
     ghosts = touched[(touched < lo) | (touched > hi)]
     owned = np.arange(lo, hi + 1, dtype=np.int64)
     local_nodes = np.concatenate([owned, ghosts])
-    g2l = np.zeros(nn + 1, dtype=np.int64)
-    g2l[local_nodes] = np.arange(1, local_nodes.size + 1)
-    conn_local = g2l[c].astype(np.int32)
+
+    def g2l(ids):                                             # global id -> 1-based local id (owned first, then ghosts)
+        ids = np.asarray(ids, dtype=np.int64)
+        out = ids - lo + 1
+        g = (ids < lo) | (ids > hi)
+        out[g] = owned.size + 1 + np.searchsorted(ghosts, ids[g])
+        return out
+
+    conn_local = g2l(c.ravel()).reshape(c.shape).astype(np.int32)
     recv, send = {}, {}
     gown = (ghosts - 1) // per
     for s in np.unique(gown):
-        recv[int(s)] = g2l[ghosts[gown == s]]
+        recv[int(s)] = g2l(ghosts[gown == s])
     # what I must send to s: my owned nodes that are ghosts on s <=> owned nodes of elements touching s-owned nodes
     oe = owner[elems]
-    for s in range(n_ranks):
+    for s in np.unique(oe):
+        s = int(s)
         if s == rank:
             continue
         has_s = (oe == s).any(axis=1)
-        if not has_s.any():
-            continue
         cand = np.unique(c[has_s])
         cand = cand[(cand >= lo) & (cand <= hi)]
         if cand.size:
-            send[s] = g2l[cand]
+            send[s] = g2l(cand)
     return Partition(rank, n_ranks, (lo, hi), local_nodes, owned.size, elems, conn_local, send, recv)
+
+
+def lattice_window(elem_type: int, dims, box, n_ranks: int, rank: int):
+    """The part of a lattice mesh (hex8_lattice / tet10_kuhn with the given dims and box) that rank `rank` of a
+    contiguous-node-range partition needs, built WITHOUT the global mesh (a 100 M-DOF lattice per process would cost
+    gigabytes and minutes): the node layers of every element that touches an owned node.  Returns
+    (window mesh, node_offset, n_nodes_global, n_elems_global); window node i+1 = global node i+1+node_offset.
+    Feed it to partition_mesh(window, P, r, node_offset, n_nodes_global)."""
+    if elem_type == HEX8:
+        nx, ny, nz = dims                                      # nodes per direction
+        h = box if np.isscalar(box) else box[0] / (nx - 1)
+        lay, nn = nx * ny, nx * ny * nz
+        per = -(-nn // n_ranks)
+        lo, hi = rank * per + 1, min((rank + 1) * per, nn)
+        ka, kb = (lo - 1) // lay, (hi - 1) // lay              # owned node layers
+        wa, wb = max(ka - 1, 0), min(kb + 1, nz - 1)
+        m = hex8_lattice(nx, ny, wb - wa + 1, h)
+        m.coords[:, 2] += wa * h
+        return m, wa * lay, nn, (nx - 1) * (ny - 1) * (nz - 1)
+    cx, cy, cz = dims
+    lx, ly, lz = box
+    px, py, pz = 2 * cx + 1, 2 * cy + 1, 2 * cz + 1
+    lay, nn = px * py, px * py * pz
+    per = -(-nn // n_ranks)
+    lo, hi = rank * per + 1, min((rank + 1) * per, nn)
+    ka, kb = (lo - 1) // lay, (hi - 1) // lay
+    ca, cb = max((ka - 1) // 2, 0), min(kb // 2, cz - 1)       # cell layers [2c, 2c+2] meeting [ka, kb]
+    m = tet10_kuhn(cx, cy, cb - ca + 1, lx, ly, lz * (cb - ca + 1) / cz)
+    m.coords[:, 2] += ca * (lz / cz)
+    return m, 2 * ca * lay, nn, 6 * cx * cy * cz
+
+
+def hashed_vector(dofs0: np.ndarray, fixed_mask: np.ndarray | None = None) -> np.ndarray:
+    """Deterministic pseudo-random test vector defined per GLOBAL 0-based dof id, so that every rank can evaluate its own
+    part without the global vector: u = 1e-3 * (2 U - 1), U = frac(golden-ratio hash of the id)."""
+    g = np.asarray(dofs0, dtype=np.uint64)
+    hsh = (g * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(11)
+    u = 1e-3 * (2.0 * (hsh.astype(np.float64) / float(1 << 53)) - 1.0)
+    if fixed_mask is not None:
+        u[fixed_mask] = 0.0
+    return u

@@ -65,6 +65,14 @@ int orc_num_threads(void) {
 #endif
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ shape functions */
 
 /* src/basis/lagrange_generated.jl:267-282 (values), expanded monomials as generated */
@@ -620,5 +628,67 @@ void orc_body_load(int et, int64_t n_nodes, int64_t n_elems, const double *X, co
             double wd = w[g] * det3(J);
             for (int k = 0; k < nn; k++) for (int c = 0; c < 3; c++) f[(int64_t)conn[e * nn + k] * 3 + c] += wd * N[k] * b[e * 3 + c];
         }
+    }
+}
+
+/* Surface elements of a 3D problem: Tri3 / Tri6 / Quad4 (Elasticity3DSurfaceElements, src/problems_elasticity.jl:454-458).
+ * Shape functions src/basis/lagrange_generated.jl:99-115 (Tri3), :127-143 (Tri6), :155-171 (Quad4), expanded as generated. */
+static void surf_shape(int nn, double u, double v, double *N, double *dN /* nn x 2 */) {
+    if (nn == 3) {
+        N[0] = 1 + -1.0 * u + -1.0 * v; N[1] = u; N[2] = v;
+        double d[6] = {-1, -1, 1, 0, 0, 1}; memcpy(dN, d, sizeof d);
+    } else if (nn == 6) {
+        N[0] = 1 + -3.0 * u + -3.0 * v + 2.0 * u * u + 4.0 * (u * v) + 2.0 * v * v;
+        N[1] = -1.0 * u + 2.0 * u * u; N[2] = -1.0 * v + 2.0 * v * v;
+        N[3] = 4.0 * u + -4.0 * u * u + -4.0 * (u * v); N[4] = 4.0 * (u * v); N[5] = 4.0 * v + -4.0 * (u * v) + -4.0 * v * v;
+        double d[12] = {-3.0 + 2.0 * (2 * u) + 4.0 * v, -3.0 + 4.0 * u + 2.0 * (2 * v), -1.0 + 2.0 * (2 * u), 0, 0, -1.0 + 2.0 * (2 * v),
+                        4.0 + -4.0 * (2 * u) + -4.0 * v, -4.0 * u, 4.0 * v, 4.0 * u, -4.0 * v, 4.0 + -4.0 * u + -4.0 * (2 * v)};
+        memcpy(dN, d, sizeof d);
+    } else {
+        N[0] = 0.25 + -0.25 * u + -0.25 * v + 0.25 * (u * v); N[1] = 0.25 + 0.25 * u + -0.25 * v + -0.25 * (u * v);
+        N[2] = 0.25 + 0.25 * u + 0.25 * v + 0.25 * (u * v); N[3] = 0.25 + -0.25 * u + 0.25 * v + -0.25 * (u * v);
+        double d[8] = {-0.25 + 0.25 * v, -0.25 + 0.25 * u, 0.25 + -0.25 * v, -0.25 + -0.25 * u, 0.25 + 0.25 * v, 0.25 + 0.25 * u,
+                       -0.25 + -0.25 * v, 0.25 + -0.25 * u};
+        memcpy(dN, d, sizeof d);
+    }
+}
+/* default rules (src/elements/integrate.jl:16,22-23): Tri3 GLTRI1, Tri6 GLTRI3 (src/quadrature/gltri.jl:7-27), Quad4 GLQUAD4 */
+static int surf_rule(int nn, double *w, double *xi /* ng x 2 */) {
+    if (nn == 3) { w[0] = 0.5; xi[0] = xi[1] = 1.0 / 3.0; return 1; }
+    if (nn == 6) {
+        double p[6] = {2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0, 2.0 / 3.0, 1.0 / 6.0, 1.0 / 6.0};
+        memcpy(xi, p, sizeof p); w[0] = w[1] = w[2] = 1.0 / 6.0; return 3;
+    }
+    const double g[2] = {-0.5773502691896258, 0.5773502691896258};
+    int q = 0;
+    for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) { xi[2 * q] = g[i]; xi[2 * q + 1] = g[j]; w[q] = 1.0; q++; }
+    return 4;
+}
+
+/* Surface traction and pressure, src/problems_elasticity.jl:454-502: per integration point w = ip.weight * detJ with
+ * detJ = || dX/dxi1 x dX/dxi2 || (src/elements/elements.jl:799-810); traction: f += w vec(T N) (:472-475);
+ * pressure: n = cross(J[:,1], J[:,2]) normalised, p = -pressure, f += w p vec(n N) (:485-491).
+ * faces: nn x n_faces 0-based node ids; traction: 3 per face or NULL; pressure: 1 per face or NULL.  f is ADDED to. */
+void orc_surface_load(int nn, int64_t n_faces, const double *X, const int32_t *faces, const double *traction, const double *pressure, double *f) {
+    double w[4], xi[8];
+    int ng = surf_rule(nn, w, xi);
+    for (int64_t fc = 0; fc < n_faces; fc++) {
+        double fe[18] = {0};
+        for (int g = 0; g < ng; g++) {
+            double N[6], dN[12], t1[3] = {0}, t2[3] = {0};
+            surf_shape(nn, xi[2 * g], xi[2 * g + 1], N, dN);
+            for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) {
+                t1[c] += dN[2 * i] * X[(int64_t)faces[fc * nn + i] * 3 + c];
+                t2[c] += dN[2 * i + 1] * X[(int64_t)faces[fc * nn + i] * 3 + c];
+            }
+            double n[3] = {t1[1] * t2[2] - t1[2] * t2[1], t1[2] * t2[0] - t1[0] * t2[2], t1[0] * t2[1] - t1[1] * t2[0]};
+            double detJ = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            double wd = w[g] * detJ;
+            for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) {
+                if (traction) fe[3 * i + c] += wd * traction[3 * fc + c] * N[i];
+                if (pressure) fe[3 * i + c] += wd * (-pressure[fc]) * (n[c] / detJ) * N[i];
+            }
+        }
+        for (int i = 0; i < nn; i++) for (int c = 0; c < 3; c++) f[(int64_t)faces[fc * nn + i] * 3 + c] += fe[3 * i + c];
     }
 }

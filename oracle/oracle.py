@@ -40,6 +40,7 @@ def lib():
         _lib = C.CDLL(build())
         L = _lib
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_shape_N.argtypes = [C.c_int, _dp, _dp]
         L.orc_shape_dN.argtypes = [C.c_int, _dp, _dp]
         L.orc_quadrature.argtypes = [C.c_int, _dp, _dp]
@@ -67,6 +68,7 @@ def lib():
         L.orc_colouring.argtypes = [C.c_int, C.c_int64, C.c_int64, _ip, _ip]
         L.orc_colouring.restype = C.c_int
         L.orc_body_load.argtypes = [C.c_int, C.c_int64, C.c_int64, _dp, _ip, _dp, _dp]
+        L.orc_surface_load.argtypes = [C.c_int, C.c_int64, _dp, _ip, C.c_void_p, C.c_void_p, _dp]
     return _lib
 
 
@@ -82,6 +84,12 @@ def _vp(a):
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle (a process started by torchrun inherits OMP_NUM_THREADS=1)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def shape_N(et, xi):
@@ -235,3 +243,74 @@ def body_load(et, coords, conn, b):
     f = np.zeros(3 * coords.shape[0])
     lib().orc_body_load(et, coords.shape[0], c0.shape[0], coords, c0, bb, f)
     return f
+
+
+def surface_load(face_type, coords, faces, traction=None, pressure=None, n_dofs=None):
+    """Consistent surface traction / pressure load vector (src/problems_elasticity.jl:454-502); faces: (n_faces, nn) 1-based."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    f0 = _conn0(np.asarray(faces).reshape(-1, face_type))
+    nf = f0.shape[0]
+    t = None if traction is None else np.ascontiguousarray(np.broadcast_to(np.asarray(traction, dtype=np.float64), (nf, 3)))
+    p = None if pressure is None else np.ascontiguousarray(np.broadcast_to(np.asarray(pressure, dtype=np.float64), (nf,)))
+    f = np.zeros(3 * coords.shape[0] if n_dofs is None else n_dofs)
+    lib().orc_surface_load(face_type, nf, coords, f0, _vp(t), _vp(p), f)
+    return f
+
+
+def quadrature_mass(et):
+    """Rule of the least-squares recovery: the next rule of the reference's integration_rule_mapping
+    (src/elements/integrate.jl:11-31) that integrates N N' exactly -- Tet4: GLTET4, Tet10: GLTET15
+    (src/quadrature/gltet.jl:44-64), Hex8: GLHEX8.  (The default rules make the Tet4 / Tet10 mass matrix singular.)"""
+    if et == 8:
+        return quadrature(8)
+    if et == 4:
+        return quadrature(10)
+    s15 = np.sqrt(15.0)
+    a, b1, b2 = 0.25, (7.0 + s15) / 34.0, (7.0 - s15) / 34.0
+    c1, c2, d, f = (13.0 - 3.0 * s15) / 34.0, (13.0 + 3.0 * s15) / 34.0, (5.0 - s15) / 20.0, (5.0 + s15) / 20.0
+    w1, w2, w3, w4 = 8.0 / 405.0, (2665.0 - 14.0 * s15) / 226800.0, (2665.0 + 14.0 * s15) / 226800.0, 5.0 / 567.0
+    pts = np.array([(a, a, a), (b1, b1, b1), (b1, b1, c1), (b1, c1, b1), (c1, b1, b1), (b2, b2, b2), (b2, b2, c2), (b2, c2, b2),
+                    (c2, b2, b2), (d, d, f), (d, f, d), (f, d, d), (d, f, f), (f, d, f), (f, f, d)])
+    return np.array([w1] + [w2] * 4 + [w3] * 4 + [w4] * 6), pts
+
+
+def lsq_recover(et, coords, conn, u, field="stress", par=(210e9, 0.3), default_rule=False):
+    """Least-squares nodal fit of the Gauss-point strain / stress (lsq_fit, src/problems_elasticity.jl:547-594):
+    A = sum w detJ N N', b_i = sum w detJ f_i N, A <- (A+A')/2, x = A \\ b (direct solve; the reference uses ldlt).
+    f = strain vector [e11,e22,e33,e12,e23,e13] with eps = (grad u' + grad u)/2 (:520-524,540-545), or the
+    linear-elastic stress la tr(eps) I + 2 mu eps of it (:527-537).  Returns (n_nodes, 6)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    c0 = _conn0(conn).astype(np.int64)
+    nn, ne = coords.shape[0], c0.shape[0]
+    X = coords[c0]                                      # (ne, nnpe, 3)
+    U = np.asarray(u, dtype=np.float64).reshape(-1, 3)[c0]
+    w, xi = quadrature(et) if default_rule else quadrature_mass(et)
+    la, mu = lame(*par[:2])
+    Ae = np.zeros((ne, et, et))
+    be = np.zeros((ne, et, 6))
+    for wg, x in zip(w, xi):
+        N, dN = shape_N(et, x), shape_dN(et, x)          # (nnpe,), (nnpe, 3)
+        J = np.einsum("ia,eib->eab", dN, X)              # J[a,b] = sum dN_i[a] X_i[b]
+        detJ = np.linalg.det(J)
+        G = np.einsum("eab,ib->eia", np.linalg.inv(J), dN)   # grad N_i = inv(J) dN_i
+        gu = np.einsum("eic,eid->ecd", U, G)             # grad u = sum u_k (x) grad N_k
+        eps = 0.5 * (gu + np.swapaxes(gu, 1, 2))
+        if field == "stress":
+            t = la * np.trace(eps, axis1=1, axis2=2)
+            eps = 2 * mu * eps + t[:, None, None] * np.eye(3)[None]
+        fv = np.stack([eps[:, 0, 0], eps[:, 1, 1], eps[:, 2, 2], eps[:, 0, 1], eps[:, 1, 2], eps[:, 0, 2]], axis=1)
+        wd = wg * detJ
+        Ae += wd[:, None, None] * (N[:, None] * N[None, :])[None]
+        be += wd[:, None, None] * N[None, :, None] * fv[:, None, :]
+    rows = np.repeat(c0, et, axis=1).ravel()
+    cols = np.tile(c0, (1, et)).ravel()
+    A = sp.coo_matrix((Ae.ravel(), (rows, cols)), shape=(nn, nn)).tocsr()
+    A = 0.5 * (A + A.T)
+    b = np.zeros((nn, 6))
+    np.add.at(b, c0.ravel(), be.reshape(-1, 6))
+    nz = np.nonzero(np.asarray(abs(A).sum(axis=1)).ravel() > 0)[0]        # get_nonzero_rows
+    x = np.zeros((nn, 6))
+    x[nz] = spla.splu(A[nz][:, nz].tocsc()).solve(b[nz])
+    return x

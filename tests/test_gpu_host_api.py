@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 def test_library_is_native_and_loaded(jf):
     from juliafem.jl_b200 import _lib
-    assert _lib.lib().jfem_abi_version() == 1
+    assert _lib.lib().jfem_abi_version() == 2
     assert "libjfem_b200.so" in open("/proc/self/maps").read()
 
 

@@ -20,7 +20,7 @@ def test_abi_exports_every_declared_symbol(jf):
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/jfem_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert _lib.lib().jfem_abi_version() == 1
+    assert _lib.lib().jfem_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure(jf):

@@ -300,3 +300,52 @@ def test_med_reader_matches_committed_fixture():
     assert set(m.elem_sets) == {"OTHER"} and m.elem_sets["OTHER"].size == m.n_elems
     with pytest.raises(ValueError):
         mesh.read_med("/root/reference/examples/linear_static/JuliaFEMSMP18.med", mesh_name="nope")
+
+
+def test_surface_load_identities(oracle):
+    """Oracle restatement of src/problems_elasticity.jl:454-502: total traction force = t * area for Tri3 / Tri6 / Quad4,
+    pressure acts against the normal dX/dxi1 x dX/dxi2, Tri3 (GLTRI1) equals the lumped area/3 rule of ext:368-416."""
+    X = np.array([[0, 0, 0], [2, 0, 0], [0, 1.5, 0], [1, 0, 0], [1, 0.75, 0], [0, 0.75, 0], [2, 1.5, 0]], float)
+    area_tri, t = 1.5, np.array([0.3, -1.0, 2.0])
+    for ft, face, area in ((3, [1, 2, 3], area_tri), (6, [1, 2, 3, 4, 5, 6], area_tri), (4, [1, 2, 7, 3], 3.0)):
+        f = oracle.surface_load(ft, X, [face], traction=t).reshape(-1, 3)
+        assert np.allclose(f.sum(0), t * area, rtol=1e-14)
+        p = oracle.surface_load(ft, X, [face], pressure=4.0).reshape(-1, 3)
+        assert np.allclose(p.sum(0), [0, 0, -4.0 * area], rtol=1e-14)        # normal = +z, positive pressure pushes -z
+    f3 = oracle.surface_load(3, X, [[1, 2, 3]], traction=t).reshape(-1, 3)
+    assert np.allclose(f3[:3], np.outer(np.full(3, area_tri / 3), t), rtol=1e-14)
+    # Tri6 consistent load of a flat straight-sided face: corners get 0, mid-side nodes a third each
+    f6 = oracle.surface_load(6, X, [[1, 2, 3, 4, 5, 6]], traction=(0, 0, 1.0)).reshape(-1, 3)[:6, 2]
+    assert np.allclose(f6, [0, 0, 0, 0.5, 0.5, 0.5], atol=1e-15)
+
+
+def test_lsq_recovery_rule_and_exactness(oracle):
+    """lsq_fit (src/problems_elasticity.jl:547-594).  With the element's default rule the Tet10 / Tet4 mass matrix is
+    singular (documented deviation: the exact rule of the reference's own rule table is used instead); with that rule a
+    linear displacement field gives its constant strain back at every node, and the stress is D : strain."""
+    import scipy.sparse as sp
+    from juliafem.jl_b200 import mesh
+    z = np.load(os.path.join(HERE, "golden", "tet10_fixture.npz"))
+    m = mesh.Mesh(10, z["coords"], z["conn"])
+    c0 = (m.conn - 1).astype(np.int64)
+    for rule, singular in ((oracle.quadrature(10), True), (oracle.quadrature_mass(10), False)):
+        A = np.zeros((m.n_nodes, m.n_nodes))
+        for wg, x in zip(*rule):
+            N, dN = oracle.shape_N(10, x), oracle.shape_dN(10, x)
+            J = np.einsum("ia,eib->eab", dN, m.coords[c0])
+            np.add.at(A, (np.repeat(c0, 10, axis=1).ravel(), np.tile(c0, (1, 10)).ravel()),
+                      ((wg * np.linalg.det(J))[:, None, None] * (N[:, None] * N[None, :])[None]).ravel())
+        ev = np.linalg.eigvalsh(0.5 * (A + A.T))
+        assert (ev[0] < 1e-12 * ev[-1]) == singular
+    w, _ = oracle.quadrature_mass(10)
+    assert abs(w.sum() - 1.0 / 6.0) < 1e-15
+    G = np.array([[1e-3, 2e-4, 0], [0, -5e-4, 3e-4], [1e-4, 0, 2e-3]])
+    u = (m.coords @ G.T).ravel()
+    eps = 0.5 * (G + G.T)
+    ev = np.array([eps[0, 0], eps[1, 1], eps[2, 2], eps[0, 1], eps[1, 2], eps[0, 2]])
+    e = oracle.lsq_recover(10, m.coords, m.conn, u, "strain")
+    assert np.abs(e - ev).max() < 1e-15
+    s = oracle.lsq_recover(10, m.coords, m.conn, u, "stress", par=(200e9, 0.3))
+    la, mu = oracle.lame(200e9, 0.3)
+    sv = 2 * mu * ev + la * ev[:3].sum() * np.array([1, 1, 1, 0, 0, 0])
+    assert relerr(s, np.tile(sv, (m.n_nodes, 1))) < 1e-12
