@@ -21,7 +21,10 @@ Prints ONE JSON line (rank 0).  Besides the contract keys:
   roofline          algorithmic bytes (35 B/DOF Tet10, 35.7 Hex8) / measured step time vs the measured HBM peak
   cpu_baseline      the reference's CPU K.v (assembled CSR SpMV, oracle port) on the SAME mesh when it fits, all host threads
   cg_time_to_solve  plain CG to ||r|| <= 1e-8 ||b|| on the 10.9 M-DOF Tet10 cantilever (N = 1) / on the workload itself (N > 1)
-  assembly          coloured CSR assembly throughput (elements/s, fraction of the 3.7 KB/element HBM roofline)
+  assembly          coloured CSR assembly throughput at 2.5 M Tet10 elements (elements/s, fraction of the 3.7 KB/element HBM
+                    roofline), pattern build time, CSR SpMV
+  plasticity        BASELINE.json configs[4]: J2 plasticity, ~30 % of the Gauss points yielding: state update + assembled tangent
+  neo_hookean       BASELINE.json configs[3]: Neo-Hookean residual / tangent K(u).v at 10.9 M DOF + a bounded Newton-Krylov sample
   hex8_weak         BASELINE.json configs[2]: Hex8 lattice, 12.5 M DOF per GPU (99.6 M DOF at N = 8), matrix-free K.u, with its
                     own parity check -- the per-N values give the weak-scaling efficiency of the 100 M-DOF target
 """
@@ -250,7 +253,9 @@ def main():
     ap.add_argument("--nccl-halo", action="store_true", help="halo through ncclSend/ncclRecv instead of peer-memory stores")
     ap.add_argument("--cg", default="auto", help="CG time-to-solve: workload name, 'same', 'none' or 'auto' (T10 at N=1, 'same' at N>1)")
     ap.add_argument("--hex8", default="auto", help="secondary Hex8 weak-scaling measurement: workload name per GPU, 'none' or 'auto' (H12)")
-    ap.add_argument("--no-extras", action="store_true", help="skip cg / assembly / hex8_weak (kernel timing only)")
+    ap.add_argument("--assembly", default="P10", choices=["P10", "small", "none"], help="assembled-path legs (N = 1): mesh size")
+    ap.add_argument("--neohooke", type=int, default=1, help="1: Neo-Hookean sample on the CG mesh (N = 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip cg / neo_hookean / assembly / plasticity / hex8_weak (kernel timing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -472,7 +477,122 @@ def main():
                 "ms_per_iteration": 1e3 * cg_s / max(cg_it, 1), "preconditioner": "none (as the reference)",
                 "setup_s": float(hh.info().setup_seconds), "gdof_iterations_per_s": 3 * pp_.n_nodes_global * cg_it / cg_s / 1e9}
 
-    cg_out = asm_out = hex_out = None
+    def guarded(fn, pair=False):
+        """the secondary legs must never take the headline line down with them: a failure is reported in place"""
+        try:
+            return fn()
+        except Exception as exc:   # noqa: BLE001
+            err = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            print(f"[bench] secondary leg failed: {err['error']}", file=sys.stderr, flush=True)
+            return (err, None) if pair else err
+
+    def timed_calls(fn, reps=5, warm=1):
+        """CUDA-event time (ms, mean) of fn(), L2 flushed before every repetition"""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for k in range(reps):
+            if flush is not None:
+                flush.fill_(float(k))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    def neo_hookean_leg(pp_, label):
+        """BASELINE.json configs[3]: Neo-Hookean finite-strain cantilever at ~10 M DOF, on the mesh of the CG leg: residual
+        f_int(u), matrix-free tangent K(u).v, and a BOUNDED Newton-Krylov sample (one Newton step, CG capped)."""
+        hh = pp_.handle
+        hh.set_material(_lib.MAT_NEO_HOOKEAN, (3.0e6, 0.45))
+        nd = 3 * pp_.local_nodes.size
+        G = 0.05 * np.random.default_rng(1).standard_normal((3, 3))
+        u = torch.from_numpy(np.ascontiguousarray((pp_.coords_local @ G.T).ravel())).to(dev)
+        f = torch.empty_like(u)
+        v = torch.from_numpy(mesh.test_vector(nd, pp_.fixed_local if pp_.fixed_local.size else None)).to(dev)
+        hh.internal_force(u, f)
+        torch.cuda.synchronize()
+        ms_r = timed_calls(lambda: hh.internal_force(u, f))
+        hh.set_linearization(u)
+        ms_t = timed_calls(lambda: hh.matvec(v, f, flags=_lib.TANGENT | _lib.PROJECT))
+        top = np.nonzero(np.abs(pp_.coords_local[:, 2] - pp_.coords_local[:, 2].max()) < 1e-12)[0]
+        fext = np.zeros(nd)
+        fext[3 * top + 2] = -3.0e3 / top.size
+        fd = torch.from_numpy(fext).to(dev)
+        cap = 300
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, nit, cgit, res, hist = hh.newton_krylov(fd, newton_tol=1e-6, max_newton=1, max_cg_per_newton=cap, forcing_max=1e-3)
+        torch.cuda.synchronize()
+        t_nk = time.perf_counter() - t0
+        return {"workload": label + " -- Neo-Hookean (E = 3e6, nu = 0.45), BASELINE.json configs[3]", "dofs": nd,
+                "residual_ms": ms_r, "residual_gdofs": nd / ms_r / 1e6, "tangent_matvec_ms": ms_t, "tangent_gdofs": nd / ms_t / 1e6,
+                "newton_krylov_sample": {"newton_steps": int(nit), "cg_iterations": int(cgit), "cg_cap_per_newton": cap, "seconds": t_nk,
+                                         "ms_per_cg_iteration": 1e3 * (t_nk - 2e-3 * ms_r) / max(int(cgit), 1), "residual_after": float(res),
+                                         "note": "bounded sample: ONE Newton step with the tangent CG capped (a converged solve at this size "
+                                                 "takes tens of thousands of CG iterations); the per-iteration cost is what scales"},
+                "l2": "flushed between repetitions" if flush is not None else "not flushed", "setup_s": float(hh.info().setup_seconds)}
+
+    def assembly_legs(size):
+        """Assembled path at P10 scale (Tet10 block 75^3 cells, 2 531 250 elements, 10.3 M DOF; 'small': 64x16x16 cells):
+        (a) linear-elastic coloured CSR assembly = `assembly`; (b) BASELINE.json configs[4]: J2 plasticity with ~30 % of the
+        Gauss points yielding -- integration-point state update (internal force) + assembled consistent tangent."""
+        peak, _ = peaks()
+        ma = mesh.tet10_kuhn(75, 75, 75, 1.0, 1.0, 1.0) if size == "P10" else mesh.tet10_kuhn(64, 16, 16, 4.0, 1.0, 1.0)
+        ha = _lib.Handle(10, ma.coords, ma.conn, device=local_rank)
+        try:
+            ha.set_material(_lib.MAT_LINEAR_ELASTIC, MAT)
+            ha.set_stream(torch.cuda.current_stream().cuda_stream)
+            ua = torch.zeros(ma.n_dofs, dtype=torch.float64, device=dev)
+            ha.matvec(ua, torch.empty_like(ua))            # patch build (needed for the internal element order) outside the pattern timing
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, nnz = ha.csr_size()                         # node adjacency + colouring on the host, pattern expansion on the device
+            t_pat = time.perf_counter() - t0
+            ms_asm = timed_calls(lambda: ha.assemble_csr(ua), reps=4)
+            v = torch.from_numpy(mesh.test_vector(ma.n_dofs)).to(dev)
+            y1, y2 = torch.empty_like(v), torch.empty_like(v)
+            ms_spmv = timed_calls(lambda: ha.spmv(v, y1), reps=4)
+            ha.matvec(v, y2)
+            torch.cuda.synchronize()
+            asm = {"workload": f"Tet10 block, {ma.n_elems} elements, {ma.n_dofs} DOF, linear elastic, coloured scatter into the reference's CSR pattern",
+                   "elements_per_s": ma.n_elems / (ms_asm * 1e-3), "ms": ms_asm, "pattern_build_s": t_pat, "nnz": nnz,
+                   "bytes_per_element": ASSEMBLY_BYTES_PER_ELEM, "frac_hbm_roofline": ASSEMBLY_BYTES_PER_ELEM * ma.n_elems / (ms_asm * 1e-3) / 1e9 / peak,
+                   "spmv_ms": ms_spmv, "spmv_gdofs": ma.n_dofs / ms_spmv / 1e6, "spmv_GBs": 12.0 * nnz / ms_spmv / 1e6,
+                   "spmv_frac_hbm": 12.0 * nnz / ms_spmv / 1e6 / peak, "spmv_vs_matfree_rel": float((y1 - y2).abs().max() / y2.abs().max()),
+                   "kernel": "one warp per element, geometry shared by the 30 columns (elem_warp_kernel)",
+                   "l2": "flushed between repetitions" if flush is not None else "not flushed"}
+            del y1, y2
+            # ---- configs[4]: uniaxial strain growing along x, so that the points with x > 0.7 yield (2 mu eps_xx > sigma_y)
+            par = (200e9, 0.3, 100e6, 10e9)
+            ha.set_material(_lib.MAT_PERFECT_PLASTICITY, par)
+            e_y = par[2] / (2.0 * par[0] / (2.0 * (1.0 + par[1])))
+            uh = np.zeros((ma.n_nodes, 3))
+            uh[:, 0] = e_y * ma.coords[:, 0] ** 2 / 1.4
+            up = torch.from_numpy(uh.ravel()).to(dev)
+            fp = torch.empty_like(up)
+            ha.internal_force(up, fp)
+            torch.cuda.synchronize()
+            ms_state = timed_calls(lambda: ha.internal_force(up, fp), reps=4)
+            ms_tan = timed_calls(lambda: ha.assemble_csr(up), reps=4)
+            ha.set_linearization(up)
+            y1, y2 = torch.empty_like(v), torch.empty_like(v)
+            ha.spmv(v, y1); ha.matvec(v, y2, flags=_lib.TANGENT)
+            torch.cuda.synchronize()
+            st = ha.get_state(committed=False)
+            pl = {"workload": f"Tet10 block, {ma.n_elems} elements, {ma.n_dofs} DOF, {4 * ma.n_elems} Gauss points, J2 plasticity with linear kinematic "
+                              "hardening (BASELINE.json configs[4])", "yielded_fraction": float(np.mean(st[:, :, 12] > 0)),
+                  "state_update_ms": ms_state, "gauss_points_per_s": 4 * ma.n_elems / (ms_state * 1e-3),
+                  "tangent_assembly_ms": ms_tan, "elements_per_s": ma.n_elems / (ms_tan * 1e-3),
+                  "frac_hbm_roofline": ASSEMBLY_BYTES_PER_ELEM * ma.n_elems / (ms_tan * 1e-3) / 1e9 / peak,
+                  "assembled_vs_matfree_tangent_rel": float((y1 - y2).abs().max() / y2.abs().max()),
+                  "l2": "flushed between repetitions" if flush is not None else "not flushed"}
+            return asm, pl
+        finally:
+            ha.close()
+
+    cg_out = asm_out = hex_out = nh_out = pl_out = cg_nh = None
     if not args.no_extras:
         cg_wl = args.cg
         if cg_wl == "auto":
@@ -482,38 +602,14 @@ def main():
         elif cg_wl != "none":
             pp2, _ = setup_problem(cg_wl)
             cg_out = cg_solve(pp2, workload_label(cg_wl, world))
+            if world == 1 and args.neohooke:
+                cg_nh = guarded(lambda: neo_hookean_leg(pp2, workload_label(cg_wl, world)))
             pp2.handle.close()
-        if world == 1:
-            # coloured CSR assembly (linear elastic Tet10, 98 304 elements): pattern build + one assembly pass
-            ma = mesh.tet10_kuhn(64, 16, 16, 4.0, 1.0, 1.0)
-            ha = _lib.Handle(10, ma.coords, ma.conn, device=local_rank)
-            ha.set_material(_lib.MAT_LINEAR_ELASTIC, MAT)
-            ha.set_stream(torch.cuda.current_stream().cuda_stream)
-            t0 = time.perf_counter()
-            ha.csr_pattern()
-            t_pat = time.perf_counter() - t0
-            ua = torch.zeros(ma.n_dofs, dtype=torch.float64, device=dev)
-            ha.assemble_csr(ua)
-            torch.cuda.synchronize()
-            ts = []
-            for k in range(5):
-                if flush is not None:
-                    flush.fill_(float(k))
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); ha.assemble_csr(ua); b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            t_asm = float(np.mean(ts)) * 1e-3
-            peak, _ = peaks()
-            asm_out = {"workload": f"Tet10 64x16x16 cells, {ma.n_elems} elements, {ma.n_dofs} DOF, linear elastic, coloured scatter into the reference's CSR pattern",
-                       "elements_per_s": ma.n_elems / t_asm, "ms": t_asm * 1e3, "pattern_build_s": t_pat,
-                       "bytes_per_element": ASSEMBLY_BYTES_PER_ELEM, "frac_hbm_roofline": ASSEMBLY_BYTES_PER_ELEM * ma.n_elems / t_asm / 1e9 / peak,
-                       "l2": "flushed between repetitions" if flush is not None else "not flushed"}
-            ha.close()
         hx = args.hex8
         if hx == "auto":
             hx = "H12" if WORKLOADS[args.workload][0] == 10 else "none"
-        if hx != "none":
+
+        def hex8_leg():
             pp3, u3 = setup_problem(hx)
             x3 = torch.from_numpy(u3).to(dev)
             y3 = torch.empty_like(x3)
@@ -522,11 +618,18 @@ def main():
             ms3 = allmax(float(t3.mean()))
             nd3 = 3 * pp3.n_nodes_global
             peak, _ = peaks()
-            hex_out = {"workload": workload_label(hx, world) + " (BASELINE.json configs[2]: 12.5 M DOF per GPU, weak scaling; 99.6 M DOF at 8 GPUs)",
+            res_hex = {"workload": workload_label(hx, world) + " (BASELINE.json configs[2]: 12.5 M DOF per GPU, weak scaling; 99.6 M DOF at 8 GPUs)",
                        "value": nd3 / (ms3 * 1e-3) / 1e9, "unit": "GDOF/s", "ms_per_step": ms3, "n_gpus": world, "dofs": nd3,
                        "roofline_frac": BYTES_PER_DOF[8] * nd3 / world / (ms3 * 1e-3) / 1e9 / peak, "parity": par3,
                        "setup_s": float(pp3.handle.info().setup_seconds), "n_patches": int(pp3.handle.info().n_patches)}
             pp3.handle.close()
+            return res_hex
+        if hx != "none":
+            hex_out = guarded(hex8_leg) if world == 1 else hex8_leg()
+        if world == 1 and cg_nh is not None:
+            nh_out = cg_nh
+        if world == 1 and args.assembly != "none":
+            asm_out, pl_out = guarded(lambda: assembly_legs(args.assembly), pair=True)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -570,6 +673,10 @@ def main():
             out["cg_time_to_solve"] = cg_out
         if asm_out is not None:
             out["assembly"] = asm_out
+        if pl_out is not None:
+            out["plasticity"] = pl_out
+        if nh_out is not None:
+            out["neo_hookean"] = nh_out
         if hex_out is not None:
             out["hex8_weak"] = hex_out
         if world == 1 and do_cpu:

@@ -242,6 +242,12 @@ class Handle:
             K = np.ascontiguousarray(np.transpose(K, (0, 2, 1)))   # column-major per element -> [row, col]
         return K, f
 
+    def csr_size(self):
+        """(n_rows, nnz) of the assembled operator; builds the pattern on the device without copying it to the host."""
+        n, nnz = C.c_int64(0), C.c_int64(0)
+        check(lib().jfem_csr_size(self._h, C.byref(n), C.byref(nnz)))
+        return int(n.value), int(nnz.value)
+
     def csr_pattern(self):
         n, nnz = C.c_int64(0), C.c_int64(0)
         check(lib().jfem_csr_size(self._h, C.byref(n), C.byref(nnz)))

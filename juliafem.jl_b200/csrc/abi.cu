@@ -128,6 +128,9 @@ int jfem_set_option(jfem_handle *h, const char *key, double value) {
         else h->timing.release();
     } else if (!strcmp(key, "warp_specialised")) {
         h->warp_specialised = value != 0;
+    } else if (!strcmp(key, "assembly_kernel")) {
+        // 1 (default): one warp per element, geometry shared by the columns; 0: one thread per (element, column)
+        h->asm_warp = value != 0;
     } else if (!strcmp(key, "async_gather")) {
         // accepted for compatibility: the gather is always asynchronous (LDGSTS.128)
     } else if (!strcmp(key, "fused_halo")) {

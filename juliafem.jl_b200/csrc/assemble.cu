@@ -9,8 +9,10 @@
 // yields column j of Ke = Km(+Kg); elements are processed colour by colour (greedy colouring, the scheme of
 // src/preprocess.jl:331-398) so that the += into vals needs no atomics and the summation order is fixed.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 
-#include "elem.cuh"
+#include "asm_elem.cuh"
 #include "handle.h"
 
 using namespace jf;
@@ -80,6 +82,59 @@ __global__ void __launch_bounds__(128) elem_columns_kernel(AsmArgs a, Pt pt) {
     if (!ok) atomicOr(a.fail, 1);
 }
 
+// One warp per element (default for the assembled path): lanes 0..NGP-1 compute the geometry of one Gauss point each
+// (grad N_k, w, and grad u for the two-field tangent functors) into shared memory, then lane j < 3*NNPE builds column j
+// of Ke from it (asm_elem.cuh) and adds its 3*NNPE entries to the CSR values (or stores them to the dense output).
+// Four elements per block; the geometry is computed once per element instead of once per column.
+template <int NNPE, class Pt>
+__global__ void __launch_bounds__(128) elem_warp_kernel(AsmArgs a, Pt pt0) {
+    constexpr int ND = 3 * NNPE, NF = Pt::NF, NGP = ElemRule<NNPE>::NGP, WPB = 4;
+    __shared__ double s_gN[WPB][NGP * 3 * NNPE];
+    __shared__ double s_Gu[WPB][NGP * 9];
+    __shared__ double s_w[WPB][NGP];
+    __shared__ int s_n[WPB][NNPE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * WPB + warp;
+    if (i >= a.ne) return;   // whole warps leave together; only __syncwarp below
+    const long long e = a.elems ? a.elems[a.e0 + i] : a.e0 + i;
+    if (lane < NNPE) s_n[warp][lane] = a.conn[e * NNPE + lane];
+    __syncwarp();
+    const int *n = s_n[warp];
+    if (lane < NGP) {
+        AField X{a.coords, n, 0, 0};
+        double *gN = &s_gN[warp][lane * 3 * NNPE];
+        s_w[warp][lane] = gp_geometry<NNPE>(lane, X, gN);
+        if (NF == 2) {
+            AField U{a.u, n, 0, 0};
+            gp_grad<NNPE>(U, gN, &s_Gu[warp][lane * 9]);
+        }
+    }
+    __syncwarp();
+    if (lane >= ND) return;
+    const int l = lane / 3, cj = lane - 3 * l;
+    const long long ei = a.e2i[e];
+    Pt pt = pt0;
+    pt.load(ei);
+    double acc[NNPE][3];
+    JF_UNROLL for (int k = 0; k < NNPE; k++) { acc[k][0] = 0.0; acc[k][1] = 0.0; acc[k][2] = 0.0; }
+    bool ok = true;
+#pragma unroll 1
+    for (int g = 0; g < NGP; g++)
+        ok &= gp_column<NNPE>(pt, ei * NGP + g, &s_gN[warp][g * 3 * NNPE], s_w[warp][g], &s_Gu[warp][g * 9], l, cj, acc);
+    if (a.vals) {
+        const uint16_t *blk = a.eblk + e * NNPE * NNPE;
+        JF_UNROLL for (int k = 0; k < NNPE; k++) {
+            const long long ap = a.adjptr[n[k]], deg = a.adjptr[n[k] + 1] - ap;
+            double *d = a.vals + 9 * ap + 3 * blk[k * NNPE + l] + cj;
+            d[0] += acc[k][0]; d[3 * deg] += acc[k][1]; d[6 * deg] += acc[k][2];
+        }
+    } else {
+        double *Ke = a.Ke + (i * ND + lane) * ND;
+        JF_UNROLL for (int k = 0; k < NNPE; k++) { Ke[3 * k] = acc[k][0]; Ke[3 * k + 1] = acc[k][1]; Ke[3 * k + 2] = acc[k][2]; }
+    }
+    if (!ok) atomicOr(a.fail, 1);
+}
+
 template <int NNPE, class Pt>
 __global__ void __launch_bounds__(128) elem_fint_kernel(AsmArgs a, Pt pt, double *fe) {
     constexpr int ND = 3 * NNPE;
@@ -145,103 +200,41 @@ __global__ void __launch_bounds__(256) spmv_kernel(long long n_rows, const long 
 // greedy element colouring (src/preprocess.jl:331-398), elements visited in ascending id; elements of one colour share no node
 int ensure_colouring(jfem_handle *h) {
     if (!h->colour_ptr.empty()) return JFEM_OK;
-    const MeshHost &m = h->mesh;
-    const int nnpe = m.nnpe;
-    const int64_t nn = m.n_nodes, ne = m.n_elems;
-    std::vector<int64_t> nptr(nn + 1, 0);
-    for (int64_t i = 0; i < ne * nnpe; i++) nptr[m.conn[i] + 1]++;
-    for (int64_t i = 0; i < nn; i++) nptr[i + 1] += nptr[i];
-    std::vector<int32_t> n2e(nptr[nn]);
-    {
-        std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
-        for (int64_t e = 0; e < ne; e++) for (int k = 0; k < nnpe; k++) n2e[fill[m.conn[e * nnpe + k]]++] = (int32_t)e;
-    }
-    std::vector<int32_t> colour(ne, -1);
-    int ncol = 0;
-    {
-        std::vector<uint8_t> used;
-        for (int64_t e = 0; e < ne; e++) {
-            used.assign(ncol + 1, 0);
-            for (int k = 0; k < nnpe; k++) {
-                const int32_t a = m.conn[e * nnpe + k];
-                for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) { int32_t c = colour[n2e[q]]; if (c >= 0) used[c] = 1; }
-            }
-            int c = 0;
-            while (used[c]) c++;
-            colour[e] = c;
-            if (c + 1 > ncol) ncol = c + 1;
-        }
-    }
-    h->colour_ptr.assign(ncol + 1, 0);
-    for (int64_t e = 0; e < ne; e++) h->colour_ptr[colour[e] + 1]++;
-    for (int c = 0; c < ncol; c++) h->colour_ptr[c + 1] += h->colour_ptr[c];
-    std::vector<int32_t> celems(ne);
-    {
-        std::vector<int64_t> fill(h->colour_ptr.begin(), h->colour_ptr.end() - 1);
-        for (int64_t e = 0; e < ne; e++) celems[fill[colour[e]]++] = (int32_t)e;
-    }
+    std::vector<int32_t> celems;
+    greedy_colouring(h->mesh, h->colour_ptr, celems);
     JFEM_TRY(h->colour_elems.upload(celems));
-    if (h->dconn.n == 0) JFEM_TRY(h->dconn.upload(m.conn));
+    if (h->dconn.n == 0) JFEM_TRY(h->dconn.upload(h->mesh.conn));
     return JFEM_OK;
 }
 
 int csr_build(jfem_handle *h) {
     if (h->csr_built) return JFEM_OK;
     JFEM_TRY(ensure_built(h));
-    const MeshHost &m = h->mesh;
-    const int nnpe = m.nnpe;
-    const int64_t nn = m.n_nodes, ne = m.n_elems;
-    // node -> elements
-    std::vector<int64_t> nptr(nn + 1, 0);
-    for (int64_t i = 0; i < ne * nnpe; i++) nptr[m.conn[i] + 1]++;
-    for (int64_t i = 0; i < nn; i++) nptr[i + 1] += nptr[i];
-    std::vector<int32_t> n2e(nptr[nn]);
-    {
-        std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
-        for (int64_t e = 0; e < ne; e++) for (int k = 0; k < nnpe; k++) n2e[fill[m.conn[e * nnpe + k]]++] = (int32_t)e;
+    auto t0 = std::chrono::steady_clock::now();
+    const int64_t nn = h->mesh.n_nodes;
+    std::vector<uint16_t> eblk;
+    {   // the (inherently sequential) greedy colouring runs on a thread of its own next to the OpenMP adjacency build
+        std::vector<int32_t> celems;
+        const bool need_colours = h->colour_ptr.empty();
+        std::thread colouring_thread;
+        if (need_colours) colouring_thread = std::thread([&] { greedy_colouring(h->mesh, h->colour_ptr, celems); });
+        const int rc = build_node_adjacency(h->mesh, h->h_nadj_ptr, h->h_nadj, eblk);   // host: hash-unique + sort per node (patches.cpp)
+        if (need_colours) colouring_thread.join();
+        if (rc != JFEM_OK) { h->colour_ptr.clear(); return rc; }
+        if (need_colours) JFEM_TRY(h->colour_elems.upload(celems));
+        if (h->dconn.n == 0) JFEM_TRY(h->dconn.upload(h->mesh.conn));
     }
-    // node adjacency
-    std::vector<int64_t> &ap = h->h_nadj_ptr;
-    ap.assign(nn + 1, 0);
-    std::vector<std::vector<int32_t>> tmp(nn);
-#pragma omp parallel for schedule(dynamic, 1024)
-    for (int64_t a = 0; a < nn; a++) {
-        std::vector<int32_t> &v = tmp[a];
-        v.reserve((nptr[a + 1] - nptr[a]) * nnpe);
-        for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) for (int k = 0; k < nnpe; k++) v.push_back(m.conn[(int64_t)n2e[q] * nnpe + k]);
-        std::sort(v.begin(), v.end());
-        v.erase(std::unique(v.begin(), v.end()), v.end());
-    }
-    for (int64_t a = 0; a < nn; a++) {
-        if (tmp[a].size() > 65535) { jfem_set_error("node %lld has more than 65535 neighbours", (long long)a); return JFEM_EINVAL; }
-        ap[a + 1] = ap[a] + (int64_t)tmp[a].size();
-    }
-    std::vector<int32_t> &adj = h->h_nadj;
-    adj.resize(ap[nn]);
-#pragma omp parallel for schedule(static)
-    for (int64_t a = 0; a < nn; a++) std::copy(tmp[a].begin(), tmp[a].end(), adj.begin() + ap[a]);
-    std::vector<std::vector<int32_t>>().swap(tmp);
-    // per element block positions
-    std::vector<uint16_t> eblk((size_t)ne * nnpe * nnpe);
-#pragma omp parallel for schedule(static)
-    for (int64_t e = 0; e < ne; e++)
-        for (int k = 0; k < nnpe; k++) {
-            const int32_t a = m.conn[e * nnpe + k];
-            const int32_t *lo = &adj[ap[a]], *hi = &adj[ap[a + 1]];
-            for (int l = 0; l < nnpe; l++)
-                eblk[(e * nnpe + k) * nnpe + l] = (uint16_t)(std::lower_bound(lo, hi, m.conn[e * nnpe + l]) - lo);
-        }
-    JFEM_TRY(ensure_colouring(h));
-    JFEM_TRY(h->nadj_ptr.upload(ap));
-    JFEM_TRY(h->nadj.upload(adj));
+    JFEM_TRY(h->nadj_ptr.upload(h->h_nadj_ptr));
+    JFEM_TRY(h->nadj.upload(h->h_nadj));
     JFEM_TRY(h->eblk.upload(eblk));
-    const int64_t nnz = 9 * ap[nn];
+    const int64_t nnz = 9 * h->h_nadj_ptr[nn];
     JFEM_TRY(h->rowptr.alloc(3 * nn + 1));
     JFEM_TRY(h->colind.alloc(nnz));
     JFEM_TRY(h->vals.alloc(nnz));
     expand_pattern_kernel<<<(unsigned)((nn + 1 + 127) / 128), 128, 0, h->stream>>>(nn, (const long long *)h->nadj_ptr.p, h->nadj.p, (long long *)h->rowptr.p, h->colind.p);
     JFEM_CUDA(cudaGetLastError());
     JFEM_CUDA(cudaStreamSynchronize(h->stream));
+    h->pattern_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     h->total_launches++;
     h->csr_built = true;
     return JFEM_OK;
@@ -256,7 +249,8 @@ template <int NNPE, class Pt>
 static int launch_columns(jfem_handle *h, AsmArgs a, const Pt &pt) {
     const long long nthreads = a.ne * 3 * NNPE;
     if (nthreads == 0) return JFEM_OK;
-    elem_columns_kernel<NNPE, Pt><<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(a, pt);
+    if (h->asm_warp) elem_warp_kernel<NNPE, Pt><<<(unsigned)((a.ne + 3) / 4), 128, 0, h->stream>>>(a, pt);
+    else elem_columns_kernel<NNPE, Pt><<<(unsigned)((nthreads + 127) / 128), 128, 0, h->stream>>>(a, pt);
     JFEM_CUDA(cudaGetLastError());
     h->total_launches++;
     return JFEM_OK;

@@ -146,4 +146,11 @@ struct MeshHost {
 };
 
 int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window, int64_t n_owned, PatchSetHost sets[N_CLASSES], InterfaceHost &iface);
+// Node adjacency of the mesh = block pattern of the reference's sparse(I, J, V) (src/sparse/sparse.jl:121-132): adj[ap[a] .. ap[a+1])
+// are the nodes sharing an element with node a, ascending; eblk[(e*nnpe+k)*nnpe+l] = position of node l of element e in the
+// row of its node k.  Returns JFEM_EINVAL if a node has more than 65535 neighbours.
+int build_node_adjacency(const MeshHost &m, std::vector<int64_t> &ap, std::vector<int32_t> &adj, std::vector<uint16_t> &eblk);
+// Greedy element colouring in ascending element id (src/preprocess.jl:331-398): elements of one colour share no node.
+// colour_ptr has n_colours+1 entries, celems lists the elements colour by colour (ascending id inside a colour).
+void greedy_colouring(const MeshHost &m, std::vector<int64_t> &colour_ptr, std::vector<int32_t> &celems);
 void classify_elements(MeshHost &m, bool use_affine);

@@ -22,6 +22,7 @@ struct jfem_handle {
     // options
     int patch_elems = 256;
     bool deterministic = true, affine = true, warp_specialised = true;
+    bool asm_warp = true;       // assembled path: one warp per element (shared geometry); false = one thread per (element, column)
     bool geometric_stiffness = false;   // option "geometric_stiffness": Kg in the St. Venant-Kirchhoff tangent (pe:378-404)
     int debug_skip = 0;                 // profiling aid (option "debug_skip"): phases of the ws kernel to leave out
     int lane_window = 48;               // candidates examined per lane by the bank-aware lane assignment (0 = off)
@@ -34,6 +35,7 @@ struct jfem_handle {
     // patches
     bool built = false;
     double setup_seconds = 0;
+    double pattern_seconds = 0;  // host + device time of csr_build (adjacency, colouring, pattern expansion)
     PatchSetHost hsets[N_CLASSES];
     InterfaceHost hif;
     PatchSetDev dsets[N_CLASSES];

@@ -12,10 +12,16 @@
 // Elements are assigned to lanes so that the 16 lanes of a half-warp hit distinct shared-memory banks as often as
 // possible (greedy, windowed): the random 64-bit gathers / scatters of the element threads are the kernel's main cost.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <numeric>
 #include <cstring>
 #include <cstdlib>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "common.h"
 
@@ -540,4 +546,142 @@ int build_patch_sets(const MeshHost &m, int EP, bool use_affine, int lane_window
     }
     if (overflow) { jfem_set_error("a node has more than 255 elements inside one patch"); return JFEM_EINVAL; }
     return JFEM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ assembled path (host side)
+
+static void node_to_elements(const MeshHost &m, std::vector<int64_t> &nptr, std::vector<int32_t> &n2e) {
+    const int nnpe = m.nnpe;
+    const int64_t nn = m.n_nodes, ne = m.n_elems;
+    nptr.assign(nn + 1, 0);
+    for (int64_t i = 0; i < ne * nnpe; i++) nptr[m.conn[i] + 1]++;
+    for (int64_t i = 0; i < nn; i++) nptr[i + 1] += nptr[i];
+    n2e.resize(nptr[nn]);
+    std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
+    for (int64_t e = 0; e < ne; e++)
+        for (int k = 0; k < nnpe; k++) n2e[fill[m.conn[e * nnpe + k]]++] = (int32_t)e;
+}
+
+int build_node_adjacency(const MeshHost &m, std::vector<int64_t> &ap, std::vector<int32_t> &adj, std::vector<uint16_t> &eblk) {
+    const int nnpe = m.nnpe;
+    const int64_t nn = m.n_nodes, ne = m.n_elems;
+    std::vector<int64_t> nptr;
+    std::vector<int32_t> n2e;
+    const bool verbose = getenv("JFEM_SETUP_TIMING") != nullptr;
+    double tt[4] = {0, 0, 0, 0};
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    tt[0] = now();
+    node_to_elements(m, nptr, n2e);
+    tt[1] = now();
+    // Every thread takes one contiguous range of nodes, sorts + uniques the candidates of each node in a scratch buffer and
+    // appends the result to its own list; the lists are then copied to their place in adj (one sort per node, no per-node
+    // allocation).
+    ap.assign(nn + 1, 0);
+    int nthr = 1;
+#ifdef _OPENMP
+    nthr = omp_get_max_threads();
+#endif
+    std::vector<std::vector<int32_t>> tbuf(nthr);
+    std::vector<int64_t> tfirst(nthr + 1, nn);
+    bool too_many = false;
+#pragma omp parallel num_threads(nthr)
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        const int64_t a0 = nn * t / nthr, a1 = nn * (t + 1) / nthr;
+        tfirst[t] = a0;
+        std::vector<int32_t> &out = tbuf[t];
+        out.reserve((size_t)((nptr[a1] - nptr[a0]) * 3 + 64));
+        // duplicates are dropped through a small open-addressing table before the sort (a Tet10 node sees ~70 candidates
+        // for ~28 distinct neighbours); only the slots that were filled are cleared again
+        std::vector<int32_t> v, table(256, -1);
+        std::vector<uint32_t> slots;
+        for (int64_t a = a0; a < a1; a++) {
+            v.clear();
+            slots.clear();
+            const size_t cand = (size_t)(nptr[a + 1] - nptr[a]) * nnpe;
+            if (table.size() < 4 * cand) { size_t sz = table.size(); while (sz < 4 * cand) sz *= 2; table.assign(sz, -1); }
+            const uint32_t msk = (uint32_t)table.size() - 1;
+            for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) {
+                const int32_t *c = &m.conn[(int64_t)n2e[q] * nnpe];
+                for (int k = 0; k < nnpe; k++) {
+                    const int32_t id = c[k];
+                    uint32_t hsh = ((uint32_t)id * 2654435761u) & msk;
+                    while (table[hsh] >= 0 && table[hsh] != id) hsh = (hsh + 1) & msk;
+                    if (table[hsh] < 0) { table[hsh] = id; v.push_back(id); slots.push_back(hsh); }
+                }
+            }
+            for (uint32_t sl : slots) table[sl] = -1;
+            std::sort(v.begin(), v.end());
+            const size_t nu = v.size();
+            if (nu > 65535) too_many = true;
+            ap[a + 1] = (int64_t)nu;
+            out.insert(out.end(), v.begin(), v.end());
+        }
+    }
+    if (too_many) { jfem_set_error("a node has more than 65535 neighbours"); return JFEM_EINVAL; }
+    for (int64_t a = 0; a < nn; a++) ap[a + 1] += ap[a];
+    adj.resize(ap[nn]);
+#pragma omp parallel for schedule(static, 1) num_threads(nthr)
+    for (int t = 0; t < nthr; t++)
+        if (!tbuf[t].empty()) std::copy(tbuf[t].begin(), tbuf[t].end(), adj.begin() + ap[tfirst[t]]);
+    std::vector<std::vector<int32_t>>().swap(tbuf);
+    tt[2] = now();
+    // block positions: the nnpe nodes of an element inside the row of each of its nodes
+    eblk.resize((size_t)ne * nnpe * nnpe);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ne; e++)
+        for (int k = 0; k < nnpe; k++) {
+            const int32_t a = m.conn[e * nnpe + k];
+            const int32_t *lo = &adj[ap[a]], *hi = lo + (ap[a + 1] - ap[a]);
+            for (int l = 0; l < nnpe; l++) eblk[(e * nnpe + k) * nnpe + l] = (uint16_t)(std::lower_bound(lo, hi, m.conn[e * nnpe + l]) - lo);
+        }
+    tt[3] = now();
+    if (verbose) fprintf(stderr, "[jfem] adjacency: node->elements %.3f s, sort/unique %.3f s, element blocks %.3f s (%d threads)\n", tt[1] - tt[0], tt[2] - tt[1], tt[3] - tt[2], nthr);
+    return JFEM_OK;
+}
+
+void greedy_colouring(const MeshHost &m, std::vector<int64_t> &colour_ptr, std::vector<int32_t> &celems) {
+    const int nnpe = m.nnpe;
+    const int64_t ne = m.n_elems;
+    std::vector<int64_t> nptr;
+    std::vector<int32_t> n2e;
+    node_to_elements(m, nptr, n2e);
+    // sequential by definition (an element takes the lowest colour none of its already coloured neighbours has); the
+    // colours of the neighbours are collected in a 64-bit mask per step, with a byte array only beyond 64 colours
+    std::vector<int32_t> colour(ne, -1);
+    int ncol = 0;
+    std::vector<uint8_t> used;
+    for (int64_t e = 0; e < ne; e++) {
+        uint64_t mask = 0;
+        for (int k = 0; k < nnpe; k++) {
+            const int32_t a = m.conn[e * nnpe + k];
+            for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) {
+                const int32_t c = colour[n2e[q]];
+                if (c >= 0 && c < 64) mask |= (1ull << c);
+            }
+        }
+        int c;
+        if (~mask) c = __builtin_ctzll(~mask);   // lowest colour below 64 that no neighbour has
+        else {                                   // all of 0..63 taken: search the higher colours
+            used.assign(ncol + 1, 0);
+            for (int k = 0; k < nnpe; k++) {
+                const int32_t a = m.conn[e * nnpe + k];
+                for (int64_t q = nptr[a]; q < nptr[a + 1]; q++) { const int32_t cc = colour[n2e[q]]; if (cc >= 0) used[cc] = 1; }
+            }
+            c = 64;
+            while (used[c]) c++;                 // used[ncol] == 0: terminates with c <= ncol (a new colour)
+        }
+        colour[e] = c;
+        if (c + 1 > ncol) ncol = c + 1;
+    }
+    colour_ptr.assign(ncol + 1, 0);
+    for (int64_t e = 0; e < ne; e++) colour_ptr[colour[e] + 1]++;
+    for (int c = 0; c < ncol; c++) colour_ptr[c + 1] += colour_ptr[c];
+    celems.resize(ne);
+    std::vector<int64_t> fill(colour_ptr.begin(), colour_ptr.end() - 1);
+    for (int64_t e = 0; e < ne; e++) celems[fill[colour[e]]++] = (int32_t)e;
 }

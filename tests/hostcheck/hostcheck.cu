@@ -180,3 +180,98 @@ extern "C" double hostcheck_build_seconds(int nnpe, long long n_nodes, long long
     }
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Replay of elem_warp_kernel (csrc/assemble.cu) for ONE element: "lanes" 0..NGP-1 run gp_geometry / gp_grad, then
+// "lanes" 0..3*NNPE-1 build one column each with gp_column (csrc/asm_elem.cuh).  Ke is column-major (as the dense output
+// of jfem_element_matrices).  kind: 0 LE, 1 Neo-Hookean, 2 J2 plasticity (st_old = 13 x NGP SoA), 3 St. Venant-Kirchhoff.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../juliafem.jl_b200/csrc/asm_elem.cuh"
+
+struct HField {   // element-local field: 3 doubles per element node
+    const double *base;
+    JF_HD double operator()(int k, int c) const { return base[3 * k + c]; }
+};
+
+template <int NNPE, class Pt>
+static bool columns_one(const Pt &pt0, const double *X, const double *u, double *Ke) {
+    constexpr int ND = 3 * NNPE, NGP = ElemRule<NNPE>::NGP;
+    double gN[NGP][3 * NNPE], Gu[NGP][9], w[NGP];
+    HField XF{X}, UF{u};
+    for (int g = 0; g < NGP; g++) {
+        w[g] = gp_geometry<NNPE>(g, XF, gN[g]);
+        if (Pt::NF == 2) gp_grad<NNPE>(UF, gN[g], Gu[g]);
+    }
+    bool ok = true;
+    for (int lane = 0; lane < ND; lane++) {
+        const int l = lane / 3, cj = lane - 3 * l;
+        Pt pt = pt0;
+        pt.load(0);
+        double acc[NNPE][3];
+        for (int k = 0; k < NNPE; k++) acc[k][0] = acc[k][1] = acc[k][2] = 0.0;
+        for (int g = 0; g < NGP; g++) ok &= gp_column<NNPE>(pt, (long long)g, gN[g], w[g], Gu[g], l, cj, acc);
+        for (int k = 0; k < NNPE; k++) for (int c = 0; c < 3; c++) Ke[(size_t)lane * ND + 3 * k + c] = acc[k][c];
+    }
+    return ok;
+}
+
+template <int NNPE>
+static int columns_kind(int kind, const double *par, int geo, const double *st_old, const double *X, const double *u, double *Ke) {
+    MatBase mb;
+    mb.la = par[0] * par[1] / ((1.0 + par[1]) * (1.0 - 2.0 * par[1])); mb.mu = par[0] / (2.0 * (1.0 + par[1]));
+    mb.sy = par[2]; mb.H = par[3]; mb.pe = nullptr; mb.pe_n = 0;
+    bool ok;
+    if (kind == 0) { PtLinear pt; static_cast<MatBase &>(pt) = mb; ok = columns_one<NNPE>(pt, X, u, Ke); }
+    else if (kind == 1) { PtNHTangent pt; static_cast<MatBase &>(pt) = mb; ok = columns_one<NNPE>(pt, X, u, Ke); }
+    else if (kind == 2) { PtPPTangent pt; static_cast<MatBase &>(pt) = mb; pt.st_old = st_old; pt.n_gp = ElemRule<NNPE>::NGP; ok = columns_one<NNPE>(pt, X, u, Ke); }
+    else { PtStVKTangent pt; static_cast<MatBase &>(pt) = mb; pt.geo = geo; ok = columns_one<NNPE>(pt, X, u, Ke); }
+    return ok ? 0 : 1;
+}
+
+extern "C" int hostcheck_element_columns(int nnpe, const double *X, const double *u, int kind, const double *par, int geo, const double *st_old,
+                                         double *Ke) {
+    if (nnpe == 10) return columns_kind<10>(kind, par, geo, st_old, X, u, Ke);
+    if (nnpe == 8) return columns_kind<8>(kind, par, geo, st_old, X, u, Ke);
+    return columns_kind<4>(kind, par, geo, st_old, X, u, Ke);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host side of the assembled path (patches.cpp: build_node_adjacency, greedy_colouring), expanded to the reference's CSR
+// pattern exactly like expand_pattern_kernel of csrc/assemble.cu.  rowptr: 3 n_nodes + 1; colind (may be null): nnz;
+// colour (may be null): colour of every element; times[0..1] = seconds of adjacency / colouring.
+// Returns nnz, or -1.  Also verifies eblk (every (k, l) entry points at node l inside the row of node k).
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" long long hostcheck_pattern(int nnpe, long long n_nodes, long long n_elems, const int32_t *conn, long long *rowptr, int32_t *colind,
+                                       int32_t *colour, double *times) {
+    MeshHost m;
+    m.nnpe = nnpe; m.n_nodes = n_nodes; m.n_elems = n_elems;
+    m.conn.assign(conn, conn + (size_t)nnpe * n_elems);
+    std::vector<int64_t> ap, cptr;
+    std::vector<int32_t> adj, celems;
+    std::vector<uint16_t> eblk;
+    auto t0 = std::chrono::steady_clock::now();
+    if (build_node_adjacency(m, ap, adj, eblk) != JFEM_OK) return -1;
+    auto t1 = std::chrono::steady_clock::now();
+    greedy_colouring(m, cptr, celems);
+    auto t2 = std::chrono::steady_clock::now();
+    if (times) { times[0] = std::chrono::duration<double>(t1 - t0).count(); times[1] = std::chrono::duration<double>(t2 - t1).count(); }
+    for (long long e = 0; e < n_elems; e++)
+        for (int k = 0; k < nnpe; k++)
+            for (int l = 0; l < nnpe; l++)
+                if (adj[ap[conn[e * nnpe + k]] + eblk[(e * nnpe + k) * nnpe + l]] != conn[e * nnpe + l]) { jfem_set_error("eblk entry wrong at element %lld", e); return -1; }
+    for (long long a = 0; a < n_nodes; a++) {
+        const long long p = ap[a], deg = ap[a + 1] - p;
+        for (int c = 0; c < 3; c++) {
+            const long long r0 = 9 * p + 3 * c * deg;
+            rowptr[3 * a + c] = r0;
+            if (colind)
+                for (long long q = 0; q < deg; q++)
+                    for (int d = 0; d < 3; d++) colind[r0 + 3 * q + d] = 3 * adj[p + q] + d;
+        }
+    }
+    rowptr[3 * n_nodes] = 9 * ap[n_nodes];
+    if (colour)
+        for (size_t c = 0; c + 1 < cptr.size(); c++)
+            for (long long q = cptr[c]; q < cptr[c + 1]; q++) colour[celems[q]] = (int32_t)c;
+    return 9 * ap[n_nodes];
+}
