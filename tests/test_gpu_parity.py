@@ -233,6 +233,55 @@ def test_csr_pattern_bit_exact_and_values(L, oracle, jf):
         assert relerr(vs, vsr) < TOL
 
 
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_assembly_kernels_against_oracle(L, oracle, jf, kernel):
+    """Both assembly kernels (option assembly_kernel: 1 = one warp per element with shared Gauss-point geometry [default],
+    0 = one thread per (element, column)) against the oracle: dense Ke of every element type, CSR values for the
+    linear-elastic, Neo-Hookean (finite strain + geometric stiffness) and plastic tangents, per-element parameters."""
+    for et, m in ((4, jf.mesh.tet4_kuhn(3, 2, 2)), (8, distorted_hex8(jf.mesh, 4)), (10, curved_tet10(jf.mesh, 3, 2, 2))):
+        h = make(L, m, assembly_kernel=kernel)
+        K, _ = h.element_matrices()
+        for e in range(0, m.n_elems, max(1, m.n_elems // 40)):
+            Ke, _, _, _ = oracle.element(et, m.coords[m.conn[e] - 1], par=LE)
+            assert relerr(K[e], Ke) < TOL
+        vals, _ = h.assemble_csr()
+        _, _, vr, _ = oracle.assemble_csr(et, m.coords, m.conn, par=LE)
+        assert relerr(vals, vr) < TOL
+        h.close()
+    m = curved_tet10(jf.mesh, 4, 3, 3)
+    rng = np.random.default_rng(11)
+    u = 0.01 * rng.standard_normal(m.n_dofs) * np.abs(m.coords).max()
+    h = make(L, m, 1, NH, assembly_kernel=kernel)
+    vals, _ = h.assemble_csr(u)
+    _, _, vr, _ = oracle.assemble_csr(10, m.coords, m.conn, u=u, kind=1, par=NH, finite_strain=True, geometric=True)
+    assert relerr(vals, vr) < 1e-11
+    h.close()
+    # plastic tangent at a yielded trial state: first step commits a state, second assembles around it
+    pp = (200e9, 0.3, 100e6, 10e9)
+    u1 = 2e-3 * rng.standard_normal(m.n_dofs) * 0.1
+    h = make(L, m, 2, pp, assembly_kernel=kernel)
+    h.internal_force(u1)
+    h.commit_state()
+    _, _, _, _, s1 = oracle.assemble_csr(10, m.coords, m.conn, u=u1, kind=2, par=pp, want_state=True)
+    assert (s1[:, :, 12] > 0).mean() > 0.2
+    u2 = u1 + 5e-5 * rng.standard_normal(m.n_dofs)
+    vals, _ = h.assemble_csr(u2)
+    _, _, vr, _ = oracle.assemble_csr(10, m.coords, m.conn, u=u2, kind=2, par=pp, state_old=s1)
+    assert relerr(vals, vr) < 1e-11
+    h.close()
+    # per-element Young's modulus / Poisson's ratio (E_vec / nu_vec of ext:135-141)
+    m = jf.mesh.tet10_kuhn(3, 2, 2)
+    par = np.stack([210e9 * (1.0 + 0.5 * rng.random(m.n_elems)), 0.2 + 0.2 * rng.random(m.n_elems)], axis=1)
+    h = L.Handle(10, m.coords, m.conn)
+    h.set_option("assembly_kernel", kernel)
+    h.set_material(0, par)
+    K, _ = h.element_matrices()
+    for e in range(0, m.n_elems, 7):
+        Ke, _, _, _ = oracle.element(10, m.coords[m.conn[e] - 1], par=tuple(par[e]))
+        assert relerr(K[e], Ke) < TOL
+    h.close()
+
+
 # ------------------------------------------------------------------------------------------------ CG
 
 def test_cg_matches_reference_iteration(L, oracle, jf):
