@@ -208,3 +208,61 @@ def test_gmsh_reader_tet10_order_sets_and_volume(tmp_path, oracle, jf):
     assert np.abs(K - K.T).max() < 1e-9 * np.abs(K).max()
     rb = np.tile([1.0, 0.0, 0.0], 10)
     assert np.abs(K @ rb).max() < 1e-9 * np.abs(K).max()
+
+
+def _split_top_level(s):
+    """split a parameter list at top-level commas"""
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_binds_declared_symbols_with_matching_arity():
+    """The Julia shim cannot be executed here (no Julia toolchain), so it is checked statically: every `ccall` names a
+    function include/jfem_b200.h declares, with as many argument types as the C prototype has parameters, and pointer /
+    integer / floating-point classes in the same positions."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "jfem_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(jfem_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = [a for a in _split_top_level(" ".join(m.group(2).split())) if a != "void"]
+        protos[m.group(1)] = args
+    jl = open(os.path.join(root, "juliafem.jl_b200", "julia", "JuliaFEMB200.jl")).read()
+    calls = list(re.finditer(r"ccall\(\(:(jfem_\w+),\s*libjfem\),\s*(\w+),\s*\(", jl))
+    assert len(calls) >= 14
+
+    def cls_c(a):
+        if "*" in a:
+            return "ptr"
+        return "flt" if re.search(r"\bdouble\b", a) else "int"
+
+    def cls_j(t):
+        if t.startswith(("Ptr", "Ref", "Cstring")):
+            return "ptr"
+        return "flt" if t in ("Cdouble", "Float64") else "int"
+
+    for m in calls:
+        name = m.group(1)
+        assert name in protos, f"{name} is not declared in include/jfem_b200.h"
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jl[i], 0)
+            i += 1
+        types = _split_top_level(jl[m.end():i - 1])
+        types = [t for t in types if t]
+        assert len(types) == len(protos[name]), f"{name}: {len(types)} ccall types vs {len(protos[name])} C parameters"
+        for t, a in zip(types, protos[name]):
+            assert cls_j(t) == cls_c(a), f"{name}: Julia type {t} bound to C parameter '{a}'"
