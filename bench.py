@@ -542,6 +542,8 @@ def main():
         ma = mesh.tet10_kuhn(75, 75, 75, 1.0, 1.0, 1.0) if size == "P10" else mesh.tet10_kuhn(64, 16, 16, 4.0, 1.0, 1.0)
         ha = _lib.Handle(10, ma.coords, ma.conn, device=local_rank)
         try:
+            for k_, v_ in (lib_opts or {}).items():
+                ha.set_option(k_, v_)
             ha.set_material(_lib.MAT_LINEAR_ELASTIC, MAT)
             ha.set_stream(torch.cuda.current_stream().cuda_stream)
             ua = torch.zeros(ma.n_dofs, dtype=torch.float64, device=dev)
@@ -561,7 +563,8 @@ def main():
                    "bytes_per_element": ASSEMBLY_BYTES_PER_ELEM, "frac_hbm_roofline": ASSEMBLY_BYTES_PER_ELEM * ma.n_elems / (ms_asm * 1e-3) / 1e9 / peak,
                    "spmv_ms": ms_spmv, "spmv_gdofs": ma.n_dofs / ms_spmv / 1e6, "spmv_GBs": 12.0 * nnz / ms_spmv / 1e6,
                    "spmv_frac_hbm": 12.0 * nnz / ms_spmv / 1e6 / peak, "spmv_vs_matfree_rel": float((y1 - y2).abs().max() / y2.abs().max()),
-                   "kernel": "one warp per element, geometry shared by the 30 columns (elem_warp_kernel)",
+                   "kernel": "one thread per (element, column) (elem_columns_kernel)" if (lib_opts or {}).get("assembly_kernel", 1) == 0
+                             else "one warp per element, geometry shared by the 30 columns (elem_warp_kernel)",
                    "l2": "flushed between repetitions" if flush is not None else "not flushed"}
             del y1, y2
             # ---- configs[4]: uniaxial strain growing along x, so that the points with x > 0.7 yield (2 mu eps_xx > sigma_y)

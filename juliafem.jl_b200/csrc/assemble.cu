@@ -122,11 +122,26 @@ __global__ void __launch_bounds__(128) elem_warp_kernel(AsmArgs a, Pt pt0) {
     for (int g = 0; g < NGP; g++)
         ok &= gp_column<NNPE>(pt, ei * NGP + g, &s_gN[warp][g * 3 * NNPE], s_w[warp][g], &s_Gu[warp][g * 9], l, cj, acc);
     if (a.vals) {
+        // read-modify-write of the 3*NNPE entries of this column, in two batches: all loads of a batch are issued before
+        // its first store (the compiler may not move a load of vals across a store to vals, so a plain `+=` per entry would
+        // serialise 3*NNPE global round trips per lane).  Elements of one colour share no node: no other warp touches these entries.
         const uint16_t *blk = a.eblk + e * NNPE * NNPE;
-        JF_UNROLL for (int k = 0; k < NNPE; k++) {
-            const long long ap = a.adjptr[n[k]], deg = a.adjptr[n[k] + 1] - ap;
-            double *d = a.vals + 9 * ap + 3 * blk[k * NNPE + l] + cj;
-            d[0] += acc[k][0]; d[3 * deg] += acc[k][1]; d[6 * deg] += acc[k][2];
+        constexpr int HALF = (NNPE + 1) / 2;
+        JF_UNROLL for (int k0 = 0; k0 < NNPE; k0 += HALF) {
+            double *d[HALF];
+            long long s3[HALF];
+            double o[HALF][3];
+            JF_UNROLL for (int q = 0; q < HALF; q++) if (k0 + q < NNPE) {
+                const int k = k0 + q;
+                const long long ap = a.adjptr[n[k]], deg = a.adjptr[n[k] + 1] - ap;
+                d[q] = a.vals + 9 * ap + 3 * blk[k * NNPE + l] + cj;
+                s3[q] = 3 * deg;
+                o[q][0] = d[q][0]; o[q][1] = d[q][s3[q]]; o[q][2] = d[q][2 * s3[q]];
+            }
+            JF_UNROLL for (int q = 0; q < HALF; q++) if (k0 + q < NNPE) {
+                const int k = k0 + q;
+                d[q][0] = o[q][0] + acc[k][0]; d[q][s3[q]] = o[q][1] + acc[k][1]; d[q][2 * s3[q]] = o[q][2] + acc[k][2];
+            }
         }
     } else {
         double *Ke = a.Ke + (i * ND + lane) * ND;
