@@ -456,6 +456,7 @@ class Analysis:
         self.converged = False
         self.residual = float("nan")
         self.history = []
+        self.results_writers = []           # src/analysis.jl:11
 
     def __call__(self, field_name, time=0.0):
         model = next(p for p in self.problems if isinstance(p.properties, Elasticity))
@@ -527,7 +528,34 @@ def run_(analysis: Analysis, tol=1e-8, relative=True, max_iter=100000, device=0,
     model.assembly.la = analysis.reactions
     for name in model.postprocess_fields:          # push!(model.postprocess_fields, "stress")  (examples/linear_static.jl:96)
         model.postprocess(name)
+    if analysis.results_writers:                   # run!(analysis) ends with write_results!(analysis) (src/solvers.jl:641-650)
+        write_results_(analysis, 0.0)
     return analysis
+
+
+def add_results_writer_(analysis: "Analysis", writer):
+    """add_results_writer!(analysis, Xdmf("results"))  (src/analysis.jl:73-76)"""
+    analysis.results_writers.append(writer)
+
+
+def write_results_(analysis: "Analysis", time=0.0):
+    """write_results!(analysis) (src/analysis.jl:91-105) -> update_xdmf!(xdmf, problem, time, fields) (src/io.jl:387-518): the
+    mesh in the caller's node order plus "displacement" and every field named in problem.postprocess_fields, as nodal data."""
+    if not analysis.results_writers:
+        import warnings
+        warnings.warn(f"No result writers attached to the analysis {analysis.name}; use add_results_writer_(analysis, Xdmf(\"results\"))")
+        return
+    from .xdmf import update_xdmf_
+    for model in (p for p in analysis.problems if isinstance(p.properties, Elasticity)):
+        d = model._data
+        if d is None or analysis.u is None:
+            raise RuntimeError("write_results_ needs a solved analysis")
+        extra = {}
+        for name in model.postprocess_fields:
+            vals = model.fields.get(name) or model.postprocess(name)
+            extra[name] = np.array([vals[int(n)] for n in d.node_ids])
+        for w in analysis.results_writers:
+            update_xdmf_(w, model.name, time, d.coords, d.conn, _NNPE[d.topology], u=analysis.u, extra=extra)
 
 
 def nodal_displacements(problem_or_data, u):

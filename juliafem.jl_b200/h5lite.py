@@ -252,3 +252,132 @@ def read(path: str) -> dict:
     with open(path, "rb") as fh:
         f = _File(fh.read())
     return f.tree(f.root[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Writer: the classic HDF5 layout (superblock version 0, version-1 object headers, root group as a symbol table = B-tree
+# v1 + local heap + one SNOD leaf, contiguous little-endian datasets).  Enough for the heavy data of the XDMF result files
+# (xdmf.py), where the reference writes flat `/DataItem_N` datasets with HDF5.jl (src/io.jl:268-312).
+# ---------------------------------------------------------------------------------------------------------------------
+
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _msg(mtype: int, body: bytes, flags: int = 0) -> bytes:
+    body = _pad8(body)
+    return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+
+def _datatype_msg(dt: np.dtype) -> bytes:
+    dt = np.dtype(dt)
+    if dt.kind == "f" and dt.itemsize in (4, 8):
+        if dt.itemsize == 8:
+            bits, props = (0x20, 63, 0), struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+        else:
+            bits, props = (0x20, 31, 0), struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+        return struct.pack("<BBBBI", 0x11, bits[0], bits[1], bits[2], dt.itemsize) + props
+    if dt.kind in "iu" and dt.itemsize in (1, 2, 4, 8):
+        return struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0x00, 0, 0, dt.itemsize) + struct.pack("<HH", 0, 8 * dt.itemsize)
+    raise H5Unsupported(f"cannot write dtype {dt}")
+
+
+def write(path: str, datasets: dict) -> None:
+    """Write `datasets` (name -> numpy array; float32/64 and integer types, any rank) as root-level contiguous datasets of a
+    new HDF5 file.  The dataspace carries the numpy (C-order) shape, as h5py would."""
+    names = sorted(datasets, key=lambda s: s.encode())
+    if not names:
+        names = []
+    for n in names:
+        if not n or "/" in n or "\0" in n:
+            raise ValueError(f"bad dataset name {n!r} (flat names only)")
+    arrays = {}
+    for n in names:
+        a = np.ascontiguousarray(datasets[n])
+        if a.dtype.byteorder == ">":
+            a = a.astype(a.dtype.newbyteorder("<"))
+        arrays[n] = a
+    leaf_k = max(4, (len(names) + 1) // 2)          # one SNOD leaf holds up to 2 * leaf_k symbols
+    internal_k = 16
+    if leaf_k > 32767:
+        raise H5Unsupported("too many datasets for a single symbol-table leaf")
+
+    # ---- local heap data: the empty string at offset 0, then the names (8-byte aligned)
+    heap = bytearray(_pad8(b"\0"))
+    name_off = {}
+    for n in names:
+        name_off[n] = len(heap)
+        heap += _pad8(n.encode() + b"\0")
+    free_off = len(heap)
+    heap += struct.pack("<QQ", 1, 16)               # one free block: next = H5HL_FREE_NULL (1), size 16
+
+    # ---- addresses (everything 8-byte aligned, laid out in file order)
+    pos = 96                                        # superblock (version 0, 8-byte offsets / lengths)
+    root_ohdr = pos
+    root_msgs = _msg(0x11, struct.pack("<QQ", 0, 0))    # patched below
+    pos += 16 + len(root_msgs)
+    heap_hdr = pos
+    pos += 32
+    heap_data = pos
+    pos += len(heap)
+    btree = pos
+    btree_size = 24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8
+    pos += btree_size
+    snod = pos
+    snod_size = 8 + 2 * leaf_k * 40
+    pos += snod_size
+    ohdr_addr, data_addr = {}, {}
+    hdrs = {}
+    for n in names:
+        a = arrays[n]
+        space = struct.pack("<BBBB4x", 1, a.ndim, 0, 0) + b"".join(struct.pack("<Q", s) for s in a.shape)
+        fill = struct.pack("<BBBB", 2, 1, 0, 0)     # version 2, early allocation, fill value undefined
+        hdrs[n] = [space, _datatype_msg(a.dtype), fill]
+        ohdr_addr[n] = pos
+        body_len = sum(len(_msg(t, b)) for t, b in zip((0x01, 0x03, 0x05), hdrs[n])) + len(_msg(0x08, b"\0" * 18))
+        pos += 16 + body_len
+    for n in names:
+        data_addr[n] = pos if arrays[n].nbytes else UNDEF
+        pos += arrays[n].nbytes + (-arrays[n].nbytes % 8)
+    eof = pos
+
+    out = bytearray()
+    # ---- superblock
+    out += b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0) + struct.pack("<HHI", leaf_k, internal_k, 0)
+    out += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    out += struct.pack("<QQII", 0, root_ohdr, 1, 0) + struct.pack("<QQ", btree, heap_hdr)     # root symbol-table entry (cached)
+    assert len(out) == 96
+    # ---- root group object header: one symbol-table message
+    root_msgs = _msg(0x11, struct.pack("<QQ", btree, heap_hdr))
+    out += struct.pack("<BBHII4x", 1, 0, 1, 1, len(root_msgs)) + root_msgs
+    # ---- local heap
+    assert len(out) == heap_hdr
+    out += b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, heap_data)
+    out += heap
+    # ---- B-tree node (group node, level 0, one child)
+    assert len(out) == btree
+    node = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if names else 0, UNDEF, UNDEF)
+    node += struct.pack("<QQQ", 0, snod, name_off[names[-1]] if names else 0)
+    out += node + b"\0" * (btree_size - len(node))
+    # ---- symbol-table leaf
+    assert len(out) == snod
+    leaf = b"SNOD" + struct.pack("<BBH", 1, 0, len(names))
+    for n in names:
+        leaf += struct.pack("<QQII16x", name_off[n], ohdr_addr[n], 0, 0)
+    out += leaf + b"\0" * (snod_size - len(leaf))
+    # ---- dataset object headers
+    for n in names:
+        assert len(out) == ohdr_addr[n]
+        a = arrays[n]
+        layout = struct.pack("<BBQQ", 3, 1, data_addr[n], a.nbytes)
+        msgs = b"".join(_msg(t, b) for t, b in zip((0x01, 0x03, 0x05), hdrs[n])) + _msg(0x08, layout)
+        out += struct.pack("<BBHII4x", 1, 0, 4, 1, len(msgs)) + msgs
+    # ---- raw data
+    for n in names:
+        a = arrays[n]
+        if a.nbytes:
+            assert len(out) == data_addr[n]
+            out += a.tobytes() + b"\0" * (-a.nbytes % 8)
+    assert len(out) == eof
+    with open(path, "wb") as fh:
+        fh.write(bytes(out))
