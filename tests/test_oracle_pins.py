@@ -349,3 +349,94 @@ def test_lsq_recovery_rule_and_exactness(oracle):
     la, mu = oracle.lame(200e9, 0.3)
     sv = 2 * mu * ev + la * ev[:3].sum() * np.array([1, 1, 1, 0, 0, 0])
     assert relerr(s, np.tile(sv, (m.n_nodes, 1))) < 1e-12
+
+
+class _HD:
+    """Hyper-dual number a + b e1 + c e2 + d e1 e2 (e1^2 = e2^2 = 0): exact first and mixed second derivatives by forward-mode
+    automatic differentiation -- what Tensors.hessian does with nested ForwardDiff duals (Tensors.jl 1.16.2, called at
+    src/materials/neo_hookean.jl:222)."""
+    __slots__ = ("a", "b", "c", "d")
+
+    def __init__(self, a, b=0.0, c=0.0, d=0.0):
+        self.a, self.b, self.c, self.d = a, b, c, d
+
+    @staticmethod
+    def lift(x):
+        return x if isinstance(x, _HD) else _HD(float(x))
+
+    def __add__(self, o):
+        o = _HD.lift(o)
+        return _HD(self.a + o.a, self.b + o.b, self.c + o.c, self.d + o.d)
+    __radd__ = __add__
+
+    def __neg__(self):
+        return _HD(-self.a, -self.b, -self.c, -self.d)
+
+    def __sub__(self, o):
+        return self + (-_HD.lift(o))
+
+    def __rsub__(self, o):
+        return _HD.lift(o) + (-self)
+
+    def __mul__(self, o):
+        o = _HD.lift(o)
+        return _HD(self.a * o.a, self.a * o.b + self.b * o.a, self.a * o.c + self.c * o.a,
+                   self.a * o.d + self.b * o.c + self.c * o.b + self.d * o.a)
+    __rmul__ = __mul__
+
+    def fn(self, f0, f1, f2):
+        """g(self) for a scalar function with value f0, first derivative f1, second derivative f2 at self.a"""
+        return _HD(f0, f1 * self.b, f1 * self.c, f1 * self.d + f2 * self.b * self.c)
+
+    def log(self):
+        return self.fn(np.log(self.a), 1.0 / self.a, -1.0 / self.a ** 2)
+
+    def sqrt(self):
+        r = np.sqrt(self.a)
+        return self.fn(r, 0.5 / r, -0.25 / (r * self.a))
+
+
+def _nh_energy_ad(mu, la, C):
+    """strain_energy(material, C) of src/materials/neo_hookean.jl:129-143, written on hyper-dual entries"""
+    I1 = C[0][0] + C[1][1] + C[2][2]
+    det = (C[0][0] * (C[1][1] * C[2][2] - C[1][2] * C[2][1]) - C[0][1] * (C[1][0] * C[2][2] - C[1][2] * C[2][0])
+           + C[0][2] * (C[1][0] * C[2][1] - C[1][1] * C[2][0]))
+    J = det.sqrt()
+    lnJ = J.log()
+    return (mu / 2.0) * (I1 - 3.0) - mu * lnJ + (la / 2.0) * (lnJ * lnJ)
+
+
+def test_nh_closed_form_equals_forward_mode_ad_of_the_energy(oracle):
+    """The reference obtains S = 2 dpsi/dC and DD = 4 d2psi/dC2 by automatic differentiation of strain_energy
+    (Tensors.hessian(psi, C, :all), src/materials/neo_hookean.jl:205-231).  Restating exactly that -- forward-mode AD of the
+    same energy expression, symmetric-tensor derivative convention (perturbations of C_ij and C_ji together, halved off the
+    diagonal) -- must give the oracle's closed form to rounding, not just to finite-difference accuracy."""
+    la, mu = oracle.lame(3e6, 0.45)
+    rng = np.random.default_rng(2024)
+    idx = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (0, 2)]
+    for trial in range(5):
+        F = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+        Cm = F.T @ F
+        Ev = np.array([0.5 * (Cm[i, j] - (i == j)) for i, j in idx])
+        S, D = oracle.nh_stress(mu, la, Ev)
+
+        def direction(i, j):          # basis of the symmetric tensors: dC = (e_i e_j' + e_j e_i') / 2
+            dC = np.zeros((3, 3))
+            dC[i, j] += 0.5
+            dC[j, i] += 0.5
+            return dC
+
+        S_ad, D_ad = np.zeros(6), np.zeros((6, 6))
+        for p, (i, j) in enumerate(idx):
+            d1 = direction(i, j)
+            for q, (k, l) in enumerate(idx):
+                d2 = direction(k, l)
+                C = [[_HD(Cm[a, b], d1[a, b], d2[a, b], 0.0) for b in range(3)] for a in range(3)]
+                psi = _nh_energy_ad(mu, la, C)
+                S_ad[p] = 2.0 * psi.b                     # S_ij = 2 dpsi/dC_ij
+                D_ad[p, q] = 4.0 * psi.d                  # DD_ijkl = 4 d2psi/dC_ij dC_kl
+        assert relerr(S, S_ad) < 1e-12
+        assert relerr(D, D_ad) < 1e-12
+        # the energy itself
+        psi0 = _nh_energy_ad(mu, la, [[_HD(Cm[a, b]) for b in range(3)] for a in range(3)]).a
+        assert abs(psi0 - oracle.nh_energy(mu, la, np.array([Cm[i, j] for i, j in idx]))) <= 1e-12 * abs(psi0)
