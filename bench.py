@@ -192,9 +192,10 @@ def run_reference(args, rank):
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_label(args.workload) + " -- CPU arm: assembled CSR K.v of the reference (oracle port), "
-                                  + ("on this very mesh" if cb["same_mesh"] else "on a bounded sample of this mesh (see cpu_baseline.sample)"),
-                      "same_mesh": cb["same_mesh"], "omp_threads": cb["cores"]},
+           "config": {"workload": workload_label(args.workload, args.gpus) + " -- CPU arm: assembled CSR K.v of the reference (oracle port), "
+                                  + ("on this very mesh" if (cb["same_mesh"] and args.gpus == 1) else
+                                     "on a bounded sample of this mesh (see cpu_baseline.sample; GDOF/s is DOF-normalised)"),
+                      "same_mesh": bool(cb["same_mesh"] and args.gpus == 1), "omp_threads": cb["cores"]},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
