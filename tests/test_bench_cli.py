@@ -28,3 +28,45 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True,
                        timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_parity_check_rows_on_a_partitioned_mesh():
+    """bench.parity_check is the in-run correctness evidence of the multi-GPU runs: every rank compares its owned rows with the
+    oracle on its local mesh (owned + ghost elements).  Replayed here without a GPU: the 'GPU result' is the oracle's K.u of
+    the WHOLE mesh restricted to the rank, so the check must pass on both the all-rows and the sampled branch (which must contain
+    interface rows), and must fail when an interface row is corrupted."""
+    import types
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from juliafem.jl_b200 import mesh as M
+    from oracle import oracle as O
+    dims, box = (3, 2, 6), (1.5, 1.0, 3.0)
+    full = M.tet10_kuhn(*dims, *box)
+    fixed = M.clamp_dofs(full)
+    gd = np.arange(full.n_dofs)
+    mask = np.zeros(full.n_dofs, dtype=bool)
+    mask[fixed - 1] = True
+    u = M.hashed_vector(gd, mask)
+    y = O.matfree(10, full.coords, full.conn, u, par=bench.MAT, fixed_dofs=fixed)
+    for rank in range(2):
+        w, off, nn, ne = M.lattice_window(10, dims, box, 2, rank)
+        p = M.partition_mesh(w, 2, rank, off, nn)
+        ldofs = (3 * (p.local_nodes[:, None] - 1) + np.arange(3)[None, :]).ravel()
+        fixed_local = np.nonzero(mask[ldofs])[0] + 1
+        pp = types.SimpleNamespace(n_owned=p.n_owned, conn_local=p.conn_local, elem_type=10, rank=rank, local_nodes=p.local_nodes,
+                                   coords_local=np.ascontiguousarray(w.coords[p.local_nodes - 1 - off]), fixed_local=fixed_local)
+        y_local, u_local = y[ldofs].copy(), u[ldofs]
+        err, n, _ = bench.parity_check(pp, y_local, u_local, 2)
+        assert n == 3 * p.n_owned and err < 1e-13
+        err, n, _ = bench.parity_check(pp, y_local, u_local, 2, full_limit=10, sample_nodes=60)
+        assert 0 < n <= 3 * 60 and err < 1e-13
+        # corrupt the row of an owned node that sits next to the partition interface: the sampled check must see it
+        ghosty = (p.conn_local > p.n_owned).any(axis=1)
+        near = np.unique(p.conn_local[ghosty])
+        near = near[near <= p.n_owned]
+        free = [k for k in near if not mask[ldofs[3 * (k - 1)]]]
+        y_bad = y_local.copy()
+        y_bad[3 * (free[0] - 1)] *= 1.0 + 1e-6
+        err_all, _, _ = bench.parity_check(pp, y_bad, u_local, 2)
+        assert err_all > 1e-12

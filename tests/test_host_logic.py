@@ -266,3 +266,30 @@ def test_julia_shim_binds_declared_symbols_with_matching_arity():
         assert len(types) == len(protos[name]), f"{name}: {len(types)} ccall types vs {len(protos[name])} C parameters"
         for t, a in zip(types, protos[name]):
             assert cls_j(t) == cls_c(a), f"{name}: Julia type {t} bound to C parameter '{a}'"
+
+
+@pytest.mark.parametrize("et,dims,box", [(10, (3, 2, 7), (1.5, 1.0, 3.5)), (8, (4, 3, 11), 0.25), (10, (2, 2, 2), (1.0, 1.0, 1.0))])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8])
+def test_lattice_window_partition_equals_partition_of_the_full_mesh(jf, et, dims, box, P):
+    """bench.py / PartitionedProblem.from_lattice build only a WINDOW of the lattice per rank (a 100 M-DOF mesh per process is
+    not affordable).  The partition computed on the window must be the partition of the whole mesh: same local nodes (owned
+    then ghosts), coordinates, local connectivity (as a set of elements, same order), send / receive lists."""
+    M = jf.mesh
+    full = M.tet10_kuhn(*dims, *box) if et == 10 else M.hex8_lattice(*dims, box)
+    elems_seen = np.zeros(full.n_elems, dtype=int)
+    for r in range(P):
+        ref = M.partition_mesh(full, P, r)
+        w, off, nn, ne = M.lattice_window(et, dims, box, P, r)
+        assert nn == full.n_nodes and ne == full.n_elems
+        got = M.partition_mesh(w, P, r, off, nn)
+        assert got.n_owned == ref.n_owned and got.owned_range == ref.owned_range
+        assert np.array_equal(got.local_nodes, ref.local_nodes)
+        assert np.allclose(w.coords[got.local_nodes - 1 - off], full.coords[ref.local_nodes - 1], rtol=0, atol=1e-13)
+        assert np.array_equal(got.conn_local, ref.conn_local)
+        assert sorted(got.send) == sorted(ref.send) and sorted(got.recv) == sorted(ref.recv)
+        for s in ref.send:
+            assert np.array_equal(got.send[s], ref.send[s])
+        for s in ref.recv:
+            assert np.array_equal(got.recv[s], ref.recv[s])
+        elems_seen[ref.elems] += 1
+    assert elems_seen.min() >= 1                                   # every element is computed by at least one rank
