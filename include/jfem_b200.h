@@ -102,6 +102,8 @@ int jfem_destroy(jfem_handle *h);
  * "fused_halo" (1: halo exchange inside the patch kernel when peer mappings exist [default]),
  * "fused_interface" (1: cooperative-launch in-kernel interface reduction; default 0, measured slower),
  * "geometric_stiffness" (props.geometric_stiffness of pe:36-46 for JFEM_MAT_STVK; default 0),
+ * "assembly_kernel" (1: one warp per element with the Gauss-point geometry shared by the columns [default], 0: one thread per
+ * (element, column)),
  * profiling aids "debug_timing", "debug_skip" */
 int jfem_set_option(jfem_handle *h, const char *key, double value);
 /* homogeneous material (per_element == 0: params has n_params entries, 2 <= n_params <= 4) or per-element
@@ -117,6 +119,9 @@ int jfem_synchronize(jfem_handle *h);
 /* --- matrix-free operator: replaces stiffness_operator_gpu / tangent_operator_gpu (ext:488-511),
  *     matrix_vector_product (eas:307-309).  y = K x (pure K.v: fixes the f_ext defect at ext:468). */
 int jfem_matvec(jfem_handle *h, const double *x, double *y, int flags, int on_device);
+/* Partitioned handles (n_ranks > 1): x and y are LOCAL vectors (owned entries first, then ghosts).  The forward halo of x happens
+ * inside the call; the GHOST entries of a device-resident x are scratch: the NCCL and the unfused peer paths overwrite them with
+ * the neighbours' values, the fused path reads the landing buffer and leaves them as they are.  Only owned entries of y are valid. */
 /* r = f_int(u) (compute_residual_gpu! ext:442-478 without the f_ext subtraction); for plasticity the
  * trial state is kept aside until jfem_commit_state (src/materials/abstract_material.jl:203-207). */
 int jfem_internal_force(jfem_handle *h, const double *u, double *f_int, int flags, int on_device);
