@@ -140,6 +140,58 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class NvmlClock:
+    """Instantaneous SM clock of one GPU through NVML (nvidia_ml_py), addressed by the UUID / PCI bus id torch reports so that
+    CUDA_VISIBLE_DEVICES renumbering cannot point it at another GPU."""
+
+    def __init__(self, props, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = None
+        for make in (lambda: pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(props.uuid)),
+                     lambda: pynvml.nvmlDeviceGetHandleByPciBusId(f"{props.pci_domain_id:08X}:{props.pci_bus_id:02X}:{props.pci_device_id:02X}.0"),
+                     lambda: pynvml.nvmlDeviceGetHandleByIndex(index)):
+            try:
+                self.h = make()
+                break
+            except Exception:
+                continue
+        if self.h is None:
+            raise RuntimeError("no NVML handle")
+
+    def read(self):
+        """(current SM MHz, maximum SM MHz)"""
+        return (float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)),
+                float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+
+
+def wait_for_clocks(step, sync, read_clock, allmin, allmax, chunk=200, max_seconds=3.0, frac=0.9):
+    """Keep every GPU busy (chunks of `chunk` steps, the SAME count on every rank: a step is a halo exchange) until the SM
+    clock of EVERY rank has reached frac x its maximum, or max_seconds have passed.  An idle B200 sits at 120 MHz; a rank that
+    has not ramped up when the timed region starts shows up as a slow rank that every neighbour then waits for.
+    read_clock() -> (mhz, max_mhz) or raises; allmin / allmax reduce a float over the ranks (collective), which also keeps
+    the loop count identical everywhere.  Returns a small report for the JSON line."""
+    t0 = time.perf_counter()
+    rounds, mhz, mx = 0, None, None
+    while True:
+        try:
+            mhz, mx = read_clock()
+            ok = 1.0 if (mx <= 0 or mhz >= frac * mx) else 0.0
+        except Exception:
+            mhz, mx, ok = None, None, 1.0              # no NVML: nothing to wait for
+        all_ok = allmin(ok)
+        elapsed = allmax(time.perf_counter() - t0)
+        if all_ok >= 1.0 or elapsed > max_seconds or rounds >= 1000:
+            break
+        for _ in range(chunk):
+            step()
+        sync()
+        rounds += 1
+    return {"extra_rounds": rounds, "extra_steps": rounds * chunk, "sm_mhz_at_start_of_timing": mhz, "sm_max_mhz": mx,
+            "all_ranks_ramped": bool(all_ok >= 1.0), "seconds": time.perf_counter() - t0}
+
+
 # ------------------------------------------------------------------------------------------------ CPU side (oracle)
 
 def cpu_baseline(workload, seconds=12.0, threads=None):
@@ -298,6 +350,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allmin(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    try:
+        nvml_clock = NvmlClock(torch.cuda.get_device_properties(local_rank), local_rank)
+    except Exception:
+        nvml_clock = None
+
+    def read_clock():
+        if nvml_clock is None:
+            raise RuntimeError("NVML unavailable")
+        return nvml_clock.read()
+
     def setup_problem(workload):
         et, dims, box = lattice_args(workload, world)
         pp = PartitionedProblem.from_lattice(et, dims, box, rank, world, local_rank, material=(_lib.MAT_LINEAR_ELASTIC, MAT), options=lib_opts)
@@ -346,6 +415,8 @@ def main():
         for _ in range(n_spin):
             step()
         torch.cuda.synchronize()
+        ramp = wait_for_clocks(step, torch.cuda.synchronize, read_clock, allmin, allmax, chunk=max(50, min(2000, n_spin // 4)),
+                               max_seconds=3.0) if spinup > 0 else None
         for _ in range(warmup):
             step()
         barrier()
@@ -400,7 +471,7 @@ def main():
             barrier()
         launches = int(h.info().total_launches) - launches_before
         times = np.array([a.elapsed_time(b) for a, b in ev])
-        return times, {"use_graph": use_graph, "host_s": host_s, "launches": launches, "t_timed": t_timed}
+        return times, {"use_graph": use_graph, "host_s": host_s, "launches": launches, "t_timed": t_timed, "clock_ramp": ramp}
 
     # ================================================================ main workload
     pp, u_host = setup_problem(args.workload)
@@ -653,7 +724,7 @@ def main():
                        "launch": "one CUDA graph replay of the K timed steps" if tinfo["use_graph"] else "per-step host launches",
                        "host_enqueue_ms_per_step": None if tinfo["host_s"] is None else tinfo["host_s"] * 1e3,
                        "per_rank_ms_mean_min_median_max": per_rank, "rank0_first_steps_ms": [round(float(v), 4) for v in times[:16]],
-                       "host_threads": host_threads()},
+                       "host_threads": host_threads(), "clock_ramp": tinfo.get("clock_ramp")},
             "parity": parity,
             "e2e": {"value": total_dofs / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * n_local_dofs, "d2h_bytes_per_step": 8 * n_local_dofs,
                     "ms_per_step": e2e_s * 1e3, "checksum_abs_y": checksum},
