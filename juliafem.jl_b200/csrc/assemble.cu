@@ -10,6 +10,7 @@
 // src/preprocess.jl:331-398) so that the += into vals needs no atomics and the summation order is fixed.
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <thread>
 
 #include "asm_elem.cuh"
@@ -233,7 +234,15 @@ int csr_build(jfem_handle *h) {
         const bool need_colours = h->colour_ptr.empty();
         std::thread colouring_thread;
         if (need_colours) colouring_thread = std::thread([&] { greedy_colouring(h->mesh, h->colour_ptr, celems); });
-        const int rc = build_node_adjacency(h->mesh, h->h_nadj_ptr, h->h_nadj, eblk);   // host: hash-unique + sort per node (patches.cpp)
+        int rc;
+        try {
+            rc = build_node_adjacency(h->mesh, h->h_nadj_ptr, h->h_nadj, eblk);   // host: hash-unique + sort per node (patches.cpp)
+        } catch (const std::exception &ex) {   // (out of memory on the host): never leave a joinable thread behind
+            if (need_colours) colouring_thread.join();
+            h->colour_ptr.clear();
+            jfem_set_error("pattern build failed: %s", ex.what());
+            return JFEM_EINVAL;
+        }
         if (need_colours) colouring_thread.join();
         if (rc != JFEM_OK) { h->colour_ptr.clear(); return rc; }
         if (need_colours) JFEM_TRY(h->colour_elems.upload(celems));

@@ -587,11 +587,12 @@ int build_node_adjacency(const MeshHost &m, std::vector<int64_t> &ap, std::vecto
     bool too_many = false;
 #pragma omp parallel num_threads(nthr)
     {
-        int t = 0;
+        int t = 0, nt = 1;   // the team may be smaller than requested: split by the ACTUAL team size
 #ifdef _OPENMP
         t = omp_get_thread_num();
+        nt = omp_get_num_threads();
 #endif
-        const int64_t a0 = nn * t / nthr, a1 = nn * (t + 1) / nthr;
+        const int64_t a0 = nn * t / nt, a1 = nn * (t + 1) / nt;
         tfirst[t] = a0;
         std::vector<int32_t> &out = tbuf[t];
         out.reserve((size_t)((nptr[a1] - nptr[a0]) * 3 + 64));
