@@ -25,6 +25,8 @@ Prints ONE JSON line (rank 0).  Besides the contract keys:
                     roofline), pattern build time, CSR SpMV
   plasticity        BASELINE.json configs[4]: J2 plasticity, ~30 % of the Gauss points yielding: state update + assembled tangent
   neo_hookean       BASELINE.json configs[3]: Neo-Hookean residual / tangent K(u).v at 10.9 M DOF + a bounded Newton-Krylov sample
+  config.clock_ramp before timing every rank is kept busy until NVML reports >= 90 % of the maximum SM clock on ALL ranks (an idle
+                    B200 sits at 120 MHz); what was seen is reported here
   hex8_weak         BASELINE.json configs[2]: Hex8 lattice, 12.5 M DOF per GPU (99.6 M DOF at N = 8), matrix-free K.u, with its
                     own parity check -- the per-N values give the weak-scaling efficiency of the 100 M-DOF target
 """
