@@ -125,13 +125,16 @@ def test_ghost_aware_patch_order_and_landing_buffer(hostcheck, oracle, jf):
     m = jf.mesh.tet10_kuhn(6, 5, 12, 1.0, 1.0, 2.0)
     u = jf.mesh.test_vector(m.n_dofs)
     yref = oracle.matfree(10, m.coords, m.conn, u, par=(210e9, 0.3)).reshape(-1, 3)
-    for rank in (0, 1):
-        p = jf.mesh.partition_mesh(m, 2, rank)
-        ml = jf.mesh.Mesh(10, m.coords[p.local_nodes - 1], p.conn_local)
-        ul = u.reshape(-1, 3)[p.local_nodes - 1].ravel()
-        y, _ = run(hostcheck, ml, ul, n_owned=p.n_owned)
-        own = y.reshape(-1, 3)[:p.n_owned]
-        assert relerr(own, yref[p.local_nodes[:p.n_owned] - 1]) < 1e-12
+    for world in (2, 3, 4):              # 3, 4: middle ranks with ghost nodes below AND above the owned range (two neighbours)
+        for rank in range(world):
+            p = jf.mesh.partition_mesh(m, world, rank)
+            ml = jf.mesh.Mesh(10, m.coords[p.local_nodes - 1], p.conn_local)
+            ul = u.reshape(-1, 3)[p.local_nodes - 1].ravel()
+            y, _ = run(hostcheck, ml, ul, n_owned=p.n_owned)
+            own = y.reshape(-1, 3)[:p.n_owned]
+            assert relerr(own, yref[p.local_nodes[:p.n_owned] - 1]) < 1e-12
+            if 0 < rank < world - 1:
+                assert len(p.recv) == 2 and len(p.send) == 2
 
 
 def test_tiny_and_empty_meshes(hostcheck, oracle, jf):
