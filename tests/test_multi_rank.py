@@ -17,7 +17,8 @@ def _free_port():
     return port
 
 
-def test_gloo_world2_halo_and_allreduce(oracle):
+@pytest.mark.parametrize("world", [2, 3])          # 3: the middle rank exchanges with two neighbours
+def test_gloo_world2_halo_and_allreduce(oracle, world):
     import torch.multiprocessing as mp
     sys.path.insert(0, HERE)
     import multirank_worker as W
@@ -25,13 +26,13 @@ def test_gloo_world2_halo_and_allreduce(oracle):
     with ctx.Manager() as mgr:
         out = mgr.dict()
         port = _free_port()
-        procs = [ctx.Process(target=W.gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+        procs = [ctx.Process(target=W.gloo_worker, args=(r, world, port, out)) for r in range(world)]
         for p in procs:
             p.start()
         for p in procs:
             p.join(120)
             assert p.exitcode == 0
-        assert len(out) == 2 and all(v[0] for v in out.values()), dict(out)
+        assert len(out) == world and all(v[0] for v in out.values()), dict(out)
 
 
 @pytest.mark.gpu
