@@ -20,7 +20,8 @@ Prints ONE JSON line (rank 0).  Besides the contract keys:
   e2e               same metric through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region)
   roofline          algorithmic bytes (35 B/DOF Tet10, 35.7 Hex8) / measured step time vs the measured HBM peak
   cpu_baseline      the reference's CPU K.v (assembled CSR SpMV, oracle port) on the SAME mesh when it fits, all host threads
-  cg_time_to_solve  plain CG to ||r|| <= 1e-8 ||b|| on the 10.9 M-DOF Tet10 cantilever (N = 1) / on the workload itself (N > 1)
+  cg_time_to_solve  plain CG to ||r|| <= 1e-8 ||b|| on the 10.9 M-DOF Tet10 cantilever (N = 1) / on the workload itself (N > 1);
+                    cg_time_to_solve_block_jacobi: the same solve with the opt-in 3x3 block-Jacobi preconditioner (N = 1)
   assembly          coloured CSR assembly throughput at 2.5 M Tet10 elements (elements/s, fraction of the 3.7 KB/element HBM
                     roofline), pattern build time, CSR SpMV
   plasticity        BASELINE.json configs[4]: J2 plasticity, ~30 % of the Gauss points yielding: state update + assembled tangent
@@ -310,6 +311,7 @@ def main():
     ap.add_argument("--hex8", default="auto", help="secondary Hex8 weak-scaling measurement: workload name per GPU, 'none' or 'auto' (H12)")
     ap.add_argument("--assembly", default="P10", choices=["P10", "small", "none"], help="assembled-path legs (N = 1): mesh size")
     ap.add_argument("--neohooke", type=int, default=1, help="1: Neo-Hookean sample on the CG mesh (N = 1)")
+    ap.add_argument("--jacobi", type=int, default=1, help="1: repeat the CG time-to-solve with the opt-in block-Jacobi preconditioner (N = 1)")
     ap.add_argument("--no-extras", action="store_true", help="skip cg / neo_hookean / assembly / plasticity / hex8_weak (kernel timing only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -540,9 +542,9 @@ def main():
         dist.all_reduce(t)
         checksum = float(t.item())
 
-    def cg_solve(pp_, label):
+    def cg_solve(pp_, label, flags=0):
         """plain (unpreconditioned) CG exactly as the reference's cg_solve_matfree_gpu!, relative stop 1e-8; uniform body
-        load in -z lumped to the nodes, clamp x = 0"""
+        load in -z lumped to the nodes, clamp x = 0.  flags = JACOBI: the opt-in 3x3 block-Jacobi PCG, same stop."""
         hh = pp_.handle
         b = np.zeros(3 * pp_.local_nodes.size)
         b[2::3] = -1.0e3
@@ -551,12 +553,14 @@ def main():
         hh.matvec(xd, torch.empty_like(xd), flags=_lib.PROJECT)    # (patch build outside the timing)
         barrier()
         t0 = time.perf_counter()
-        _, cg_it, cg_res = hh.cg(bd, x0=xd, tol=1e-8, relative=True, max_iter=200000)
+        _, cg_it, cg_res = hh.cg(bd, x0=xd, tol=1e-8, relative=True, max_iter=200000, flags=flags)
         torch.cuda.synchronize()
         cg_s = allmax(time.perf_counter() - t0)
         return {"workload": label, "dofs": 3 * pp_.n_nodes_global, "iterations": int(cg_it), "seconds": cg_s, "final_abs_residual": float(cg_res),
                 "converged": bool(cg_it < 200000), "tol": "||r|| <= 1e-8 ||b|| (relative; the reference's default is absolute 1e-6)",
-                "ms_per_iteration": 1e3 * cg_s / max(cg_it, 1), "preconditioner": "none (as the reference)",
+                "ms_per_iteration": 1e3 * cg_s / max(cg_it, 1),
+                "preconditioner": "3x3 block-Jacobi (opt-in, not in the reference; the time includes building the blocks)" if flags & _lib.JACOBI
+                                  else "none (as the reference)",
                 "setup_s": float(hh.info().setup_seconds), "gdof_iterations_per_s": 3 * pp_.n_nodes_global * cg_it / cg_s / 1e9}
 
     def guarded(fn, pair=False):
@@ -677,7 +681,7 @@ def main():
         finally:
             ha.close()
 
-    cg_out = asm_out = hex_out = nh_out = pl_out = cg_nh = None
+    cg_out = asm_out = hex_out = nh_out = pl_out = cg_nh = jac_out = None
     if not args.no_extras:
         cg_wl = args.cg
         if cg_wl == "auto":
@@ -715,6 +719,16 @@ def main():
             nh_out = cg_nh
         if world == 1 and args.assembly != "none":
             asm_out, pl_out = guarded(lambda: assembly_legs(args.assembly), pair=True)
+        if world == 1 and args.jacobi and cg_wl not in ("none",):
+            # last leg (a failure here cannot take another leg with it): the same solve with the block-Jacobi preconditioner
+            def jacobi_leg():
+                wl = args.workload if cg_wl == "same" else cg_wl
+                pp4, _ = setup_problem(wl)
+                try:
+                    return cg_solve(pp4, workload_label(wl, world), flags=_lib.JACOBI)
+                finally:
+                    pp4.handle.close()
+            jac_out = guarded(jacobi_leg)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -756,6 +770,8 @@ def main():
                 pass
         if cg_out is not None:
             out["cg_time_to_solve"] = cg_out
+        if jac_out is not None:
+            out["cg_time_to_solve_block_jacobi"] = jac_out
         if asm_out is not None:
             out["assembly"] = asm_out
         if pl_out is not None:
