@@ -29,15 +29,17 @@ def main():
         mesh = M.Mesh(10, z["coords"], z["conn"])
     # model = Problem(Elasticity, "OTHER", 3); model_elements = create_elements(mesh, "OTHER")   (:26-27; Seg3 / Tri6 filtered, :35-39)
     model = A.Problem(A.Elasticity, "OTHER", 3)
-    model_elements = [A.Element(A.Tet10, c, fields={"geometry": mesh.coords[c - 1].T}) for c in mesh.conn]
+    model_elements = A.create_elements(mesh, "OTHER")
     A.update_(model_elements, "youngs modulus", 208.0e3)                                  # :28
     A.update_(model_elements, "poissons ratio", 0.30)                                     # :29
     A.update_(model_elements, "density", 7.80e-9)                                         # :30
     A.add_elements_(model, model_elements)                                                # :31
     # nodes with |y - 50| <= 6 plus the three nodes nearest to the dot of the "i"           (:46-72)
-    mid_fixed = np.union1d(M.nodes_at_plane(mesh, 1, 50.0), M.find_nearest_nodes(mesh, [165.0, 88.0, 10], 3))
+    A.add_node_to_node_set_(mesh, "mid_fixed", *M.nodes_at_plane(mesh, 1, 50.0))        # :58
+    A.add_node_to_node_set_(mesh, "mid_fixed", *M.find_nearest_nodes(mesh, [165.0, 88.0, 10], 3))   # :64-67
+    mid_fixed = mesh.node_sets["mid_fixed"]
     fixed = A.Problem(A.Dirichlet, "fixed", 3, "displacement")                            # :76
-    fixed_elements = [A.Element(A.Poi1, [int(n)]) for n in mid_fixed]                     # :77
+    fixed_elements = A.create_nodal_elements(mesh, "mid_fixed")                           # :77
     A.add_elements_(fixed, fixed_elements)                                                # :78
     for c in (1, 2, 3):                                                                   # :79-81
         A.update_(fixed_elements, f"displacement {c}", 0.0)

@@ -106,6 +106,35 @@ def update_(elements, name, value):
         el.fields[name] = value
 
 
+# ---- mesh -> elements helpers of the reference's preprocessing layer (src/preprocess.jl:83-89,210-262, src/io/abaqus_reader.jl:62-67)
+
+def add_node_to_node_set_(mesh, set_name, *node_ids):
+    """add_node_to_node_set!(mesh, :name, nids...)  (src/preprocess.jl:83-89); mesh = juliafem.jl_b200.mesh.Mesh"""
+    cur = set(int(n) for n in mesh.node_sets.get(set_name, ()))
+    cur.update(int(n) for n in node_ids)
+    mesh.node_sets[set_name] = np.array(sorted(cur), dtype=np.int64)
+
+
+def create_elements(mesh, *element_sets):
+    """create_elements(mesh, "OTHER", ...)  (src/preprocess.jl:210-262): volume elements of the named element sets (all
+    elements without a name; a name the mesh has no set for, like MED's family-0 "OTHER" of a mesh without groups, means all),
+    each with its "geometry" field (3 x nnpe) and its element id."""
+    topo = {4: Tet4, 8: Hex8, 10: Tet10}[int(mesh.elem_type)]
+    ids = None
+    for name in element_sets:
+        if name in mesh.elem_sets:
+            sel = np.asarray(mesh.elem_sets[name], dtype=np.int64)
+            ids = sel if ids is None else np.union1d(ids, sel)
+    if ids is None:
+        ids = np.arange(1, mesh.n_elems + 1, dtype=np.int64)
+    return [Element(topo, mesh.conn[e - 1], fields={"geometry": mesh.coords[mesh.conn[e - 1] - 1].T}, id=int(e)) for e in ids]
+
+
+def create_nodal_elements(mesh, node_set_name):
+    """create_nodal_elements(mesh, "mid_fixed")  (src/io/abaqus_reader.jl:62-67): one Poi1 element per node of the set"""
+    return [Element(Poi1, [int(n)], fields={"geometry": mesh.coords[int(n) - 1][:, None]}) for n in mesh.node_sets[node_set_name]]
+
+
 def _nodes_by_rows(X, nn):
     """The reference stores element geometry as a 3 x nnpe matrix (one column per node, ext/JuliaFEMCUDAExt.jl:117);
     an (nnpe, 3) array is accepted too when unambiguous."""

@@ -293,3 +293,20 @@ def test_lattice_window_partition_equals_partition_of_the_full_mesh(jf, et, dims
             assert np.array_equal(got.recv[s], ref.recv[s])
         elems_seen[ref.elems] += 1
     assert elems_seen.min() >= 1                                   # every element is computed by at least one rank
+
+
+def test_preprocess_helpers_of_the_api_mirror(jf):
+    """create_elements / create_nodal_elements / add_node_to_node_set! as examples/linear_static.jl:26-27,58-77 uses them."""
+    from juliafem.jl_b200 import api as A
+    m = jf.mesh.tet10_kuhn(2, 1, 1)
+    m.elem_sets["LEFT"] = np.array([1, 2, 3])
+    m.elem_sets["RIGHT"] = np.array([3, 7])
+    els = A.create_elements(m, "OTHER")                         # no such set: every element (MED family 0)
+    assert len(els) == m.n_elems and els[4].id == 5 and els[4].connectivity == tuple(int(c) for c in m.conn[4])
+    assert els[0].fields["geometry"].shape == (3, 10) and np.array_equal(els[0].fields["geometry"].T, m.coords[m.conn[0] - 1])
+    assert [e.id for e in A.create_elements(m, "LEFT", "RIGHT")] == [1, 2, 3, 7]
+    A.add_node_to_node_set_(m, "fixed", 5, 2)
+    A.add_node_to_node_set_(m, "fixed", 2, 9)
+    assert list(m.node_sets["fixed"]) == [2, 5, 9]
+    pois = A.create_nodal_elements(m, "fixed")
+    assert [p.topology for p in pois] == [A.Poi1] * 3 and [p.connectivity for p in pois] == [(2,), (5,), (9,)]
