@@ -16,19 +16,23 @@
  *   element integration  src/problems_elasticity.jl:203-451 (Voigt BL, Km += w BL' D BL, f_int += w BL' s)
  *   block-form check     src/physics/assembly_helpers.jl:201-226, :263-283
  *   materials            src/materials/linear_elastic.jl:82,97,136-158
- *                        src/materials/neo_hookean.jl:129-143,205-231 (AD replaced by closed form, self-checked by FD)
+ *                        src/materials/neo_hookean.jl:129-143,205-231 (AD replaced by closed form, checked against forward-mode AD and FD)
  *                        src/materials/perfect_plasticity.jl:247-357
  *   scatter / pattern    src/sparse/sparse.jl:53-55,121-132,178-181 ; src/assembly/problems.jl:466-478
  *   symmetrisation       src/solvers.jl:289-292
  *   Dirichlet + CG       ext/JuliaFEMCUDAExt.jl:423-435,531-577 ; src/backend/cpu.jl:221-254
  *
- * PARITY PIN STATUS: the reference cannot run here (no Julia; package does not load as
- * shipped) and its own test-suite for this path is absent from the snapshot, so the only
- * pins are the known-answer values that survive in its docs/comments (tests/golden/pins.json:
- * LE uniaxial/shear, PP return-map values, the Tet10 consistent-mass table of
- * src/assembly/assembly.jl:139-149, quadrature sums).  Element stiffness entries, the CSR
- * pattern, K.u and CG solutions have no surviving golden file: for those, PARITY IS UNPINNED
- * by the reference's own tests and rests on this restatement plus analytic identities.
+ * PARITY PIN STATUS: the reference cannot run here (no Julia; the package does not load as shipped).  Pinned against values
+ * the reference itself holds (tests/golden/pins.json, tests/test_oracle_pins.py):
+ *   - END TO END: examples/linear_static.jl:133, max |u| = 2.4052929896922337 on JuliaFEMSMP18.med (Tet10 shape functions and
+ *     node order, GLTET4, D, scatter + dof numbering, consistent body load, Dirichlet elimination, solve) -- reproduced by this
+ *     oracle to 6e-12 relative and by the GPU path to 1e-8 (tests/test_gpu_host_api.py);
+ *   - LE uniaxial / shear / tangent identity, PP return-map values + on-surface identity, the Tet10 consistent-mass table of
+ *     src/assembly/assembly.jl:139-149, quadrature constants, the reference's tet10.inp fixture mesh;
+ *   - Neo-Hookean: the closed form below equals second-order forward-mode AD of the reference's strain_energy (what
+ *     Tensors.hessian computes, neo_hookean.jl:222) to 1e-12.
+ * Not pinned by a reference-held value (none survives in the snapshot): individual Ke entries, CSR values and K.u of other
+ * meshes; those rest on this restatement plus analytic identities (symmetry, rigid modes, patch test, block form == Voigt form).
  *
  * Layout conventions: node coordinates X[i*3+b]; element connectivity conn[e*nnpe+k], 0-based
  * here (the Python wrapper converts from the reference's 1-based ids); dof = 3*node + c
