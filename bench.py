@@ -173,25 +173,26 @@ def wait_for_clocks(step, sync, read_clock, allmin, allmax, chunk=200, max_secon
     """Keep every GPU busy (chunks of `chunk` steps, the SAME count on every rank: a step is a halo exchange) until the SM
     clock of EVERY rank has reached frac x its maximum, or max_seconds have passed.  An idle B200 sits at 120 MHz; a rank that
     has not ramped up when the timed region starts shows up as a slow rank that every neighbour then waits for.
+    The clock is read while the chunk is still executing (the steps are only enqueued), i.e. under load.
     read_clock() -> (mhz, max_mhz) or raises; allmin / allmax reduce a float over the ranks (collective), which also keeps
     the loop count identical everywhere.  Returns a small report for the JSON line."""
     t0 = time.perf_counter()
-    rounds, mhz, mx = 0, None, None
+    rounds, mhz, mx, all_ok = 0, None, None, 1.0
     while True:
+        for _ in range(chunk):
+            step()
         try:
             mhz, mx = read_clock()
             ok = 1.0 if (mx <= 0 or mhz >= frac * mx) else 0.0
         except Exception:
             mhz, mx, ok = None, None, 1.0              # no NVML: nothing to wait for
+        sync()
+        rounds += 1
         all_ok = allmin(ok)
         elapsed = allmax(time.perf_counter() - t0)
         if all_ok >= 1.0 or elapsed > max_seconds or rounds >= 1000:
             break
-        for _ in range(chunk):
-            step()
-        sync()
-        rounds += 1
-    return {"extra_rounds": rounds, "extra_steps": rounds * chunk, "sm_mhz_at_start_of_timing": mhz, "sm_max_mhz": mx,
+    return {"rounds": rounds, "steps": rounds * chunk, "sm_mhz_under_load": mhz, "sm_max_mhz": mx,
             "all_ranks_ramped": bool(all_ok >= 1.0), "seconds": time.perf_counter() - t0}
 
 

@@ -74,24 +74,27 @@ def test_bench_parity_check_rows_on_a_partitioned_mesh():
 
 def test_clock_ramp_guard_logic():
     """bench.wait_for_clocks keeps the GPUs busy until every rank reports >= 90 % of its maximum SM clock (collective decision,
-    same step count on every rank) and gives up after max_seconds; without NVML it does nothing."""
+    same step count on every rank; the clock is read while a chunk is in flight) and gives up after max_seconds; without
+    NVML it runs its single chunk and stops."""
     sys.path.insert(0, ROOT)
     import bench
     ident = lambda v: float(v)
     steps = []
-    # already at full clock: no extra work
+    # already at full clock: one chunk (extra warm-up), then stop
     r = bench.wait_for_clocks(lambda: steps.append(1), lambda: None, lambda: (1965.0, 1965.0), ident, ident, chunk=10)
-    assert r["extra_rounds"] == 0 and r["all_ranks_ramped"] and not steps
+    assert r["rounds"] == 1 and r["all_ranks_ramped"] and len(steps) == 10
     # ramps up while we keep it busy
+    steps.clear()
     clocks = iter([(120.0, 1965.0), (900.0, 1965.0), (1965.0, 1965.0)])
     r = bench.wait_for_clocks(lambda: steps.append(1), lambda: None, lambda: next(clocks), ident, ident, chunk=10)
-    assert r["extra_rounds"] == 2 and len(steps) == 20 and r["all_ranks_ramped"] and r["sm_mhz_at_start_of_timing"] == 1965.0
+    assert r["rounds"] == 3 and len(steps) == 30 and r["all_ranks_ramped"] and r["sm_mhz_under_load"] == 1965.0
     # another rank is still slow (allmin says no) although this one is fine: keeps going until the time limit
     steps.clear()
     r = bench.wait_for_clocks(lambda: steps.append(1), lambda: None, lambda: (1965.0, 1965.0), lambda v: 0.0, ident, chunk=5, max_seconds=0.05)
-    assert not r["all_ranks_ramped"] and r["extra_rounds"] >= 1 and len(steps) == 5 * r["extra_rounds"]
+    assert not r["all_ranks_ramped"] and r["rounds"] >= 1 and len(steps) == 5 * r["rounds"]
     # no NVML: nothing to wait for
     def broken():
         raise RuntimeError("NVML unavailable")
-    r = bench.wait_for_clocks(lambda: steps.append(1), lambda: None, broken, ident, ident)
-    assert r["extra_rounds"] == 0 and r["sm_mhz_at_start_of_timing"] is None
+    steps.clear()
+    r = bench.wait_for_clocks(lambda: steps.append(1), lambda: None, broken, ident, ident, chunk=7)
+    assert r["rounds"] == 1 and len(steps) == 7 and r["sm_mhz_under_load"] is None and r["all_ranks_ramped"]

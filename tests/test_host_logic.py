@@ -310,3 +310,26 @@ def test_preprocess_helpers_of_the_api_mirror(jf):
     assert list(m.node_sets["fixed"]) == [2, 5, 9]
     pois = A.create_nodal_elements(m, "fixed")
     assert [p.topology for p in pois] == [A.Poi1] * 3 and [p.connectivity for p in pois] == [(2,), (5,), (9,)]
+
+
+def test_argument_validation_at_the_abi_without_a_device(jf):
+    """Edge cases the C ABI refuses before it ever touches a device (so they can be checked here): null / empty inputs, a bad
+    index base, more nodes than the 27-bit node ids of the patch tables can hold, and calls on a null handle."""
+    import ctypes as C
+    from juliafem.jl_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    xyz = np.zeros(3)
+    ptr = xyz.ctypes.data_as(C.c_void_p)
+    def err():
+        return L.jfem_last_error().decode()
+    assert L.jfem_create(C.byref(h), 0, 10, 0, 0, ptr, None, 1) == 1 and "bad arguments" in err()          # no nodes
+    assert L.jfem_create(C.byref(h), 0, 10, 1, 0, None, None, 1) == 1                                        # null coordinates
+    assert L.jfem_create(C.byref(h), 0, 10, 1, 1, ptr, None, 1) == 1                                         # elements without connectivity
+    assert L.jfem_create(C.byref(h), 0, 10, 1, 0, ptr, None, 2) == 1                                         # index base must be 0 or 1
+    assert L.jfem_create(None, 0, 10, 1, 0, ptr, None, 1) == 1 and "null output" in err()
+    assert L.jfem_create(C.byref(h), 0, 10, 1 << 27, 0, ptr, None, 1) == 1 and "nodes per handle" in err()   # maximum size
+    assert h.value is None
+    assert L.jfem_set_option(None, b"patch_elems", 256.0) == 1 and "null handle" in err()
+    assert L.jfem_matvec(None, ptr, ptr, 0, 0) == 1
+    assert L.jfem_destroy(None) in (0, 1)                                                                     # harmless
