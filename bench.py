@@ -28,6 +28,8 @@ Prints ONE JSON line (rank 0).  Besides the contract keys:
   neo_hookean       BASELINE.json configs[3]: Neo-Hookean residual / tangent K(u).v at 10.9 M DOF + a bounded Newton-Krylov sample
   config.clock_ramp before timing every rank is kept busy until NVML reports >= 90 % of the maximum SM clock on ALL ranks (an idle
                     B200 sits at 120 MHz); what was seen is reported here
+  linear_static     BASELINE.json configs[0]: examples/linear_static.jl end to end on the GPU against the value the reference holds
+                    (max |u| = 2.4052929896922337) + the CPU assemble / direct-solve time of the same problem
   hex8_weak         BASELINE.json configs[2]: Hex8 lattice, 12.5 M DOF per GPU (99.6 M DOF at N = 8), matrix-free K.u, with its
                     own parity check -- the per-N values give the weak-scaling efficiency of the 100 M-DOF target
 """
@@ -312,6 +314,7 @@ def main():
     ap.add_argument("--hex8", default="auto", help="secondary Hex8 weak-scaling measurement: workload name per GPU, 'none' or 'auto' (H12)")
     ap.add_argument("--assembly", default="P10", choices=["P10", "small", "none"], help="assembled-path legs (N = 1): mesh size")
     ap.add_argument("--neohooke", type=int, default=1, help="1: Neo-Hookean sample on the CG mesh (N = 1)")
+    ap.add_argument("--linear-static", type=int, default=1, help="1: the reference's examples/linear_static.jl end to end against its own expected value (N = 1)")
     ap.add_argument("--jacobi", type=int, default=1, help="1: repeat the CG time-to-solve with the opt-in block-Jacobi preconditioner (N = 1)")
     ap.add_argument("--no-extras", action="store_true", help="skip cg / neo_hookean / assembly / plasticity / hex8_weak (kernel timing only)")
     args = ap.parse_args()
@@ -682,7 +685,52 @@ def main():
         finally:
             ha.close()
 
-    cg_out = asm_out = hex_out = nh_out = pl_out = cg_nh = jac_out = None
+    def linear_static_leg():
+        """BASELINE.json configs[0] = examples/linear_static.jl of the reference, the one end-to-end value the reference itself holds
+        (max |u| = 2.4052929896922337, :133): committed copy of its mesh (tests/golden/linear_static_smp18.npz), E = 208e3,
+        nu = 0.3, body load 1.0 in x, the clamp of :46-72; consistent load on the device, projected CG to 1e-12.  CPU side: the
+        oracle's assembly + a sparse direct solve (scipy splu) as the stand-in for the reference's LDLt (src/solvers.jl:205-210)."""
+        z = np.load(os.path.join(ROOT, "tests", "golden", "linear_static_smp18.npz"))
+        m = mesh.Mesh(10, z["coords"], z["conn"])
+        nodes = np.union1d(mesh.nodes_at_plane(m, 1, 50.0, 6.0), mesh.find_nearest_nodes(m, [165.0, 88.0, 10.0], 3))
+        fixed = np.sort((3 * (nodes[:, None] - 1) + np.arange(1, 4)[None, :]).ravel())
+        ref = 2.4052929896922337
+        t0 = time.perf_counter()
+        hl = _lib.Handle(10, m.coords, m.conn, device=local_rank)
+        try:
+            hl.set_material(_lib.MAT_LINEAR_ELASTIC, (208.0e3, 0.30))
+            hl.set_dirichlet(fixed)
+            hl.set_stream(torch.cuda.current_stream().cuda_stream)
+            f = hl.body_load((1.0, 0.0, 0.0))
+            u, it, res = hl.cg(f, tol=1e-12, relative=True, max_iter=200000)
+            torch.cuda.synchronize()
+            t_gpu = time.perf_counter() - t0
+        finally:
+            hl.close()
+        umax = float(np.linalg.norm(np.asarray(u).reshape(-1, 3), axis=1).max())
+        out_ = {"workload": f"examples/linear_static.jl (BASELINE.json configs[0]): {m.n_nodes} nodes, {m.n_elems} Tet10, {fixed.size} fixed dofs",
+                "max_u_norm": umax, "reference_value": ref, "rel_err": abs(umax / ref - 1.0), "tol": 1.5e-8,
+                "ok": bool(abs(umax / ref - 1.0) < 1.5e-8), "cg_iterations": int(it), "final_abs_residual": float(res),
+                "gpu_seconds_setup_load_solve": t_gpu,
+                "note": "reference value and tolerance: @test isapprox(maximum(values(u_norms)), 2.4052929896922337), examples/linear_static.jl:133"}
+        if do_cpu:
+            import scipy.sparse as sp
+            import scipy.sparse.linalg as spla
+            from oracle import oracle as O
+            O.set_num_threads(host_threads())
+            t0 = time.perf_counter()
+            rp, ci, vals, _ = O.assemble_csr(10, m.coords, m.conn, par=(208.0e3, 0.30), symmetrise=True)
+            fc = O.body_load(10, m.coords, m.conn, (1.0, 0.0, 0.0))
+            K = sp.csr_matrix((vals, ci, rp))
+            free = np.setdiff1d(np.arange(m.n_dofs), fixed - 1)
+            uc = np.zeros(m.n_dofs)
+            uc[free] = spla.splu(K[free][:, free].tocsc()).solve(fc[free])
+            out_["cpu_seconds_assemble_direct_solve"] = time.perf_counter() - t0
+            out_["cpu_max_u_norm"] = float(np.linalg.norm(uc.reshape(-1, 3), axis=1).max())
+            out_["gpu_vs_cpu_field_rel"] = float(np.abs(np.asarray(u) - uc).max() / np.abs(uc).max())
+        return out_
+
+    cg_out = asm_out = hex_out = nh_out = pl_out = cg_nh = jac_out = ls_out = None
     if not args.no_extras:
         cg_wl = args.cg
         if cg_wl == "auto":
@@ -720,6 +768,8 @@ def main():
             nh_out = cg_nh
         if world == 1 and args.assembly != "none":
             asm_out, pl_out = guarded(lambda: assembly_legs(args.assembly), pair=True)
+        if world == 1 and args.linear_static:
+            ls_out = guarded(linear_static_leg)
         if world == 1 and args.jacobi and cg_wl not in ("none",):
             # last leg (a failure here cannot take another leg with it): the same solve with the block-Jacobi preconditioner
             def jacobi_leg():
@@ -773,6 +823,8 @@ def main():
             out["cg_time_to_solve"] = cg_out
         if jac_out is not None:
             out["cg_time_to_solve_block_jacobi"] = jac_out
+        if ls_out is not None:
+            out["linear_static"] = ls_out
         if asm_out is not None:
             out["assembly"] = asm_out
         if pl_out is not None:
